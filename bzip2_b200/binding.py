@@ -1,0 +1,187 @@
+"""ctypes loader for libbz2_b200.so (include/bz2_b200.h and include/bzlib.h)."""
+import ctypes as C
+import os
+import subprocess
+import functools
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libbz2_b200.so")
+
+BZ_RUN, BZ_FLUSH, BZ_FINISH = 0, 1, 2
+BZ_OK, BZ_RUN_OK, BZ_FLUSH_OK, BZ_FINISH_OK, BZ_STREAM_END = 0, 1, 2, 3, 4
+BZ_SEQUENCE_ERROR, BZ_PARAM_ERROR, BZ_MEM_ERROR, BZ_OUTBUFF_FULL, BZ_CONFIG_ERROR = -1, -2, -3, -8, -9
+
+
+class Bz2B200Error(RuntimeError):
+    pass
+
+
+class Stats(C.Structure):
+    _fields_ = [("in_bytes", C.c_uint64), ("out_bytes", C.c_uint64), ("n_blocks", C.c_uint32),
+                ("n_windows", C.c_uint32), ("sum_nblock", C.c_uint64), ("sum_nmtf", C.c_uint64),
+                ("n_power_blocks", C.c_uint32), ("combined_crc", C.c_uint32),
+                ("ms_total", C.c_float), ("ms_s1", C.c_float), ("ms_s2", C.c_float), ("ms_s3", C.c_float),
+                ("ms_s4", C.c_float), ("bwt_rounds", C.c_uint32), ("kernel_launches", C.c_uint32)]
+
+
+class BzStream(C.Structure):
+    _fields_ = [("next_in", C.c_void_p), ("avail_in", C.c_uint), ("total_in_lo32", C.c_uint),
+                ("total_in_hi32", C.c_uint), ("next_out", C.c_void_p), ("avail_out", C.c_uint),
+                ("total_out_lo32", C.c_uint), ("total_out_hi32", C.c_uint), ("state", C.c_void_p),
+                ("bzalloc", C.c_void_p), ("bzfree", C.c_void_p), ("opaque", C.c_void_p)]
+
+
+def build_library(verbose=False):
+    """Compile every CUDA source for sm_100a (nvcc cross-compiles without a GPU)."""
+    out = None if verbose else subprocess.DEVNULL
+    subprocess.check_call(["make", "-C", os.path.join(HERE, "csrc"), "-j8"], stdout=out)
+    return LIB_PATH
+
+
+EXPORTS = [
+    # include/bz2_b200.h
+    "bz2b200_device_count", "bz2b200_last_error", "bz2b200_version", "bz2b200_engine_create",
+    "bz2b200_engine_destroy", "bz2b200_compress_host", "bz2b200_compress_device", "bz2b200_stream_begin",
+    "bz2b200_stream_feed", "bz2b200_debug_keep", "bz2b200_debug_fetch",
+    # include/bzlib.h
+    "BZ2_bzCompressInit", "BZ2_bzCompress", "BZ2_bzCompressEnd", "BZ2_bzBuffToBuffCompress",
+    "BZ2_bzWriteOpen", "BZ2_bzWrite", "BZ2_bzWriteClose", "BZ2_bzWriteClose64", "BZ2_bzlibVersion",
+]
+
+
+@functools.lru_cache(None)
+def load():
+    if not os.path.exists(LIB_PATH):
+        raise Bz2B200Error(f"{LIB_PATH} is missing: run __graft_entry__.build() (there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, sz = C.c_void_p, C.c_size_t
+    lib.bz2b200_device_count.restype = C.c_int
+    lib.bz2b200_last_error.restype = C.c_char_p
+    lib.bz2b200_version.restype = C.c_char_p
+    lib.bz2b200_engine_create.restype = C.c_int
+    lib.bz2b200_engine_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, sz]
+    lib.bz2b200_engine_destroy.restype = None
+    lib.bz2b200_engine_destroy.argtypes = [vp]
+    lib.bz2b200_compress_host.restype = C.c_int
+    lib.bz2b200_compress_host.argtypes = [vp, vp, sz, vp, C.POINTER(sz), C.c_uint, C.POINTER(Stats)]
+    lib.bz2b200_compress_device.restype = C.c_int
+    lib.bz2b200_compress_device.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz), C.c_uint, C.POINTER(Stats)]
+    lib.bz2b200_stream_begin.restype = C.c_int
+    lib.bz2b200_stream_begin.argtypes = [vp]
+    lib.bz2b200_debug_keep.restype = C.c_int
+    lib.bz2b200_debug_keep.argtypes = [vp, C.c_int]
+    lib.bz2b200_debug_fetch.restype = C.c_int
+    lib.bz2b200_debug_fetch.argtypes = [vp, C.c_char_p, vp, sz, C.POINTER(sz)]
+    lib.BZ2_bzCompressInit.restype = C.c_int
+    lib.BZ2_bzCompressInit.argtypes = [C.POINTER(BzStream), C.c_int, C.c_int, C.c_int]
+    lib.BZ2_bzCompress.restype = C.c_int
+    lib.BZ2_bzCompress.argtypes = [C.POINTER(BzStream), C.c_int]
+    lib.BZ2_bzCompressEnd.restype = C.c_int
+    lib.BZ2_bzCompressEnd.argtypes = [C.POINTER(BzStream)]
+    lib.BZ2_bzBuffToBuffCompress.restype = C.c_int
+    lib.BZ2_bzBuffToBuffCompress.argtypes = [vp, C.POINTER(C.c_uint), vp, C.c_uint, C.c_int, C.c_int, C.c_int]
+    lib.BZ2_bzlibVersion.restype = C.c_char_p
+    lib.bz2b200_pool_clear.restype = None
+    return lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise Bz2B200Error(f"{what} failed: rc={rc}: {load().bz2b200_last_error().decode()}")
+
+
+def _ptr(a):
+    return a.ctypes.data if a.size else None
+
+
+class Engine:
+    """One GPU compression engine (bz2b200_engine_*)."""
+
+    def __init__(self, level=9, device=0, window_bytes=0):
+        self.lib = load()
+        self.h = C.c_void_p()
+        self.level = level
+        _check(self.lib.bz2b200_engine_create(C.byref(self.h), device, level, window_bytes), "engine_create")
+
+    def close(self):
+        if self.h:
+            self.lib.bz2b200_engine_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def compress(self, data, flags=0):
+        a = np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray)) else np.ascontiguousarray(data, np.uint8)
+        cap = int(a.size * 1.02) + 24576 * (a.size // (100000 * self.level - 19) + 2) + 1024
+        out = np.empty(cap, np.uint8)
+        n = C.c_size_t(cap)
+        st = Stats()
+        _check(self.lib.bz2b200_compress_host(self.h, _ptr(a), a.size, out.ctypes.data, C.byref(n), flags, C.byref(st)),
+               "compress_host")
+        self.stats = st
+        return out[: n.value].tobytes()
+
+    def compress_device(self, d_src_ptr, n, d_dst_ptr, dst_cap, flags=0):
+        """Input and output are device pointers (e.g. torch tensor .data_ptr())."""
+        out_len = C.c_size_t(0)
+        st = Stats()
+        _check(self.lib.bz2b200_compress_device(self.h, d_src_ptr, n, d_dst_ptr, dst_cap, C.byref(out_len), flags, C.byref(st)),
+               "compress_device")
+        self.stats = st
+        return out_len.value
+
+    def fetch(self, name, dtype, count=None):
+        cap = (1 << 28)
+        dt = np.dtype(dtype)
+        # ask for the natural size first
+        buf = np.empty(cap // dt.itemsize if count is None else count, dtype=dt)
+        got = C.c_size_t(0)
+        _check(self.lib.bz2b200_debug_fetch(self.h, name.encode(), buf.ctypes.data, buf.nbytes, C.byref(got)), f"debug_fetch({name})")
+        return buf[: got.value // dt.itemsize].copy()
+
+
+def compress(data, level=9):
+    """BZ2_bzBuffToBuffCompress through the libbz2-compatible entry point."""
+    lib = load()
+    a = np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray)) else np.ascontiguousarray(data, np.uint8)
+    cap = int(a.size * 1.02) + 24576 * (a.size // (100000 * level - 19) + 2) + 1024
+    out = np.empty(cap, np.uint8)
+    n = C.c_uint(cap)
+    src = a.ctypes.data if a.size else out.ctypes.data
+    rc = lib.BZ2_bzBuffToBuffCompress(out.ctypes.data, C.byref(n), src, a.size, level, 0, 0)
+    if rc != BZ_OK:
+        raise Bz2B200Error(f"BZ2_bzBuffToBuffCompress rc={rc}: {lib.bz2b200_last_error().decode()}")
+    return out[: n.value].tobytes()
+
+
+class bzlib:
+    """Streaming API mirror (BZ2_bzCompressInit / BZ2_bzCompress / BZ2_bzCompressEnd) for tests."""
+
+    def __init__(self, level=9):
+        self.lib = load()
+        self.strm = BzStream()
+        rc = self.lib.BZ2_bzCompressInit(C.byref(self.strm), level, 0, 0)
+        if rc != BZ_OK:
+            raise Bz2B200Error(f"BZ2_bzCompressInit rc={rc}: {self.lib.bz2b200_last_error().decode()}")
+        self.out = bytearray()
+
+    def call(self, data, action, out_chunk=1 << 16):
+        """One BZ2_bzCompress call; returns (rc, consumed)."""
+        a = np.frombuffer(bytes(data), dtype=np.uint8).copy() if len(data) else np.zeros(1, np.uint8)
+        ob = np.empty(out_chunk, np.uint8)
+        self.strm.next_in = a.ctypes.data
+        self.strm.avail_in = len(data)
+        self.strm.next_out = ob.ctypes.data
+        self.strm.avail_out = out_chunk
+        rc = self.lib.BZ2_bzCompress(C.byref(self.strm), action)
+        produced = out_chunk - self.strm.avail_out
+        self.out += ob[:produced].tobytes()
+        return rc, len(data) - self.strm.avail_in
+
+    def end(self):
+        return self.lib.BZ2_bzCompressEnd(C.byref(self.strm))

@@ -1,0 +1,477 @@
+// engine.cu -- window orchestration and the C ABI declared in include/bz2_b200.h.
+//
+// Host-side driver of the five stages.  The path it replaces in the reference is
+// handle_compress (bzlib.c:361-396) looping copy_input_until_stop + BZ2_compressBlock
+// one 900 kB block at a time; here a window of up to ~100 blocks is taken through each
+// stage with one set of kernel launches.
+#include "engine.h"
+#include "../../include/bz2_b200.h"
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+
+namespace bz {
+
+static thread_local char g_err[256] = "";
+
+int engine_fail(Engine* e, cudaError_t c, const char* file, int line)
+{
+   const char* base = strrchr(file, '/');
+   snprintf(g_err, sizeof g_err, "CUDA error %d (%s) at %s:%d", (int)c, cudaGetErrorString(c), base ? base + 1 : file, line);
+   if (e) snprintf(e->err, sizeof e->err, "%s", g_err);
+   return BZ2B200_ECUDA;
+}
+
+static int set_err(int code, const char* msg)
+{
+   snprintf(g_err, sizeof g_err, "%s", msg);
+   return code;
+}
+
+// ---- stream state kept between windows -----------------------------------------------------
+struct StreamState {
+   u64 bits;            // absolute stream bits produced so far
+   u32 combined_crc;    // compress.c:826-828
+   u32 block_no;
+   bool header_done;
+   bool tail_running;   // last byte arrived in BZ_RUN mode
+   // host-side bit carry for the host/stream paths
+   u8  carry; u32 ncarry;
+   size_t h_fill;       // bytes waiting in h_in
+   bz2b200_stats st;
+};
+
+struct EngineFull : Engine {
+   StreamState ss;
+   bool debug_keep;
+   u32 last_nb, last_E;
+   cudaEvent_t ev[6];
+};
+
+template <typename T>
+static cudaError_t dalloc(T** p, size_t count)
+{
+   return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
+}
+
+#define ALLOC(ptr, count) do { cudaError_t c_ = dalloc(&(ptr), (size_t)(count)); if (c_ != cudaSuccess) { rc = engine_fail(e, c_, __FILE__, __LINE__); goto fail; } } while (0)
+
+static void engine_free(EngineFull* e)
+{
+   if (!e) return;
+   cudaSetDevice(e->device);
+   void* dev[] = { e->enc, e->cend, e->sa, e->rank, e->nrank, e->keyA, e->keyB, e->idxB, e->bwt, e->z, e->mtfv, e->hist,
+                   e->blockmap, e->tile_len, e->tile_ext, e->tile_carry, e->tile_size, e->tile_base, e->s1_scalars,
+                   e->mtf_summary, e->mtf_tilemeta, e->mtf_tilecnt, e->sel, e->hlen, e->hfreq, e->hcode, e->grpbits,
+                   e->pre, e->prebits, e->ngroups, e->d_in, e->d_out,
+                   e->bt.X, e->bt.P, e->bt.crc, e->bt.origptr, e->bt.power_q, e->bt.inuse, e->bt.ninuse, e->bt.nmtf,
+                   e->bt.mtffreq, e->bt.bits, e->bt.bitoff, e->lists.counts[0], e->lists.counts[1] };
+   for (void* p : dev) if (p) cudaFree(p);
+   for (int w = 0; w < 2; w++) {
+      for (int c = 0; c < N_SMALL_CLASSES; c++) if (e->lists.small_items[w][c]) cudaFree(e->lists.small_items[w][c]);
+      for (int c = 0; c < 3; c++) if (e->lists.big_items[w][c]) cudaFree(e->lists.big_items[w][c]);
+   }
+   if (e->h_scalars) cudaFreeHost(e->h_scalars);
+   if (e->h_counts) cudaFreeHost(e->h_counts);
+   if (e->h_blk) cudaFreeHost(e->h_blk);
+   if (e->h_in) cudaFreeHost(e->h_in);
+   if (e->h_out) cudaFreeHost(e->h_out);
+   for (int i = 0; i < 6; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+   if (e->stream) cudaStreamDestroy(e->stream);
+   free(e);
+}
+
+static int engine_new(EngineFull** out, int device, int level, size_t window_bytes)
+{
+   int ndev = 0;
+   cudaError_t ce = cudaGetDeviceCount(&ndev);
+   if (ce != cudaSuccess || ndev == 0) return set_err(BZ2B200_ENODEV, "no CUDA device available (this library has no CPU path)");
+   if (device < 0 || device >= ndev) return set_err(BZ2B200_EPARAM, "bad device index");
+   if (level < 1 || level > 9) return set_err(BZ2B200_EPARAM, "block_size_100k must be 1..9");
+   EngineFull* e = static_cast<EngineFull*>(calloc(1, sizeof(EngineFull)));
+   if (!e) return set_err(BZ2B200_ENOMEM, "out of host memory");
+   int rc = 0;
+   e->device = device; e->level = level; e->nmax = 100000u * (u32)level - 19u;
+   if (cudaSetDevice(device) != cudaSuccess) { free(e); return set_err(BZ2B200_ENODEV, "cudaSetDevice failed"); }
+   {
+      cudaDeviceProp prop;
+      cudaGetDeviceProperties(&prop, device);
+      e->num_sms = prop.multiProcessorCount;
+   }
+   if (window_bytes == 0) window_bytes = (size_t)96 << 20;
+   // a window must be able to hold the input of one full block of pure runs (255 -> 5 bytes)
+   const size_t min_win = (size_t)(e->nmax + 16) * 52;
+   if (window_bytes < min_win) window_bytes = min_win;
+   if (window_bytes > ((size_t)100 << 20)) window_bytes = (size_t)100 << 20;   // 1.25*W must stay below 2^27
+   e->win_cap = (u32)window_bytes;
+   e->enc_cap = (u32)(window_bytes + window_bytes / 4 + 4096);
+   e->blk_cap = e->enc_cap / e->nmax + 2;
+   if (e->blk_cap > MAX_BLOCKS) e->blk_cap = MAX_BLOCKS;
+   {
+      const size_t E = e->enc_cap, B = e->blk_cap;
+      const size_t tiles_max = (e->nmax + 16 + MTF_TILE - 1) / MTF_TILE;
+      const size_t ntiles = window_bytes / 4096 + 4;
+      cudaError_t c0 = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+      if (c0 != cudaSuccess) { rc = engine_fail(e, c0, __FILE__, __LINE__); goto fail; }
+      for (int i = 0; i < 6; i++) cudaEventCreate(&e->ev[i]);
+      ALLOC(e->enc, E + 64); ALLOC(e->cend, E + 64);
+      ALLOC(e->sa, E + 64); ALLOC(e->rank, E + 64); ALLOC(e->nrank, E + 64);
+      ALLOC(e->keyA, E + 64); ALLOC(e->keyB, E + 64); ALLOC(e->idxB, E + 64);
+      ALLOC(e->bwt, E + 64); ALLOC(e->z, E + 64); ALLOC(e->mtfv, E + B + 64);
+      ALLOC(e->hist, B * 65536);
+      ALLOC(e->blockmap, E / 4096 + 4);
+      ALLOC(e->tile_len, ntiles); ALLOC(e->tile_ext, ntiles); ALLOC(e->tile_carry, ntiles);
+      ALLOC(e->tile_size, ntiles); ALLOC(e->tile_base, ntiles);
+      ALLOC(e->s1_scalars, 16);
+      ALLOC(e->mtf_summary, B * tiles_max * 256);
+      ALLOC(e->mtf_tilemeta, B * tiles_max * 5);
+      ALLOC(e->mtf_tilecnt, B * tiles_max);
+      ALLOC(e->sel, E / 50 + 2 * B + 64);
+      ALLOC(e->grpbits, E / 50 + 2 * B + 64);
+      ALLOC(e->hlen, B * 6 * BZ_MAX_ALPHA); ALLOC(e->hfreq, B * 6 * BZ_MAX_ALPHA); ALLOC(e->hcode, B * 6 * BZ_MAX_ALPHA);
+      ALLOC(e->pre, B * 24576); ALLOC(e->prebits, B); ALLOC(e->ngroups, B);
+      ALLOC(e->bt.X, B + 2); ALLOC(e->bt.P, B + 2); ALLOC(e->bt.crc, B); ALLOC(e->bt.origptr, B); ALLOC(e->bt.power_q, B);
+      ALLOC(e->bt.inuse, B * 256); ALLOC(e->bt.ninuse, B); ALLOC(e->bt.nmtf, B); ALLOC(e->bt.mtffreq, B * BZ_MAX_ALPHA);
+      ALLOC(e->bt.bits, B); ALLOC(e->bt.bitoff, B + 2);
+      static const u32 minlen[N_SMALL_CLASSES] = {2, 3, 5, 9, 17};
+      for (int c = 0; c < N_SMALL_CLASSES; c++) e->lists.small_cap[c] = (u32)(E / minlen[c] + 1024);
+      e->lists.big_cap[0] = (u32)(E / 33 + 1024); e->lists.big_cap[1] = (u32)(E / 513 + 1024); e->lists.big_cap[2] = (u32)(E / 4097 + 1024);
+      for (int w = 0; w < 2; w++) {
+         for (int c = 0; c < N_SMALL_CLASSES; c++) ALLOC(e->lists.small_items[w][c], e->lists.small_cap[c]);
+         for (int c = 0; c < 3; c++) ALLOC(e->lists.big_items[w][c], e->lists.big_cap[c]);
+         ALLOC(e->lists.counts[w], N_CLASSES);
+      }
+      e->out_cap = E + E / 32 + B * 24576 + 4096;
+      e->out_cap = (e->out_cap + 255) & ~(size_t)255;
+      // device/host staging is allocated lazily by the host and stream paths
+   }
+   {
+      cudaError_t c1 = cudaMallocHost(reinterpret_cast<void**>(&e->h_scalars), 64 * sizeof(u32));
+      cudaError_t c2 = cudaMallocHost(reinterpret_cast<void**>(&e->h_counts), 16 * sizeof(u32));
+      cudaError_t c3 = cudaMallocHost(reinterpret_cast<void**>(&e->h_blk), (size_t)e->blk_cap * 4 * sizeof(u32) + 64);
+      if (c1 != cudaSuccess || c2 != cudaSuccess || c3 != cudaSuccess) { rc = set_err(BZ2B200_ENOMEM, "pinned host allocation failed"); goto fail; }
+   }
+   *out = e;
+   return 0;
+fail:
+   engine_free(e);
+   return rc ? rc : BZ2B200_ENOMEM;
+}
+
+static int ensure_staging(EngineFull* e, bool need_hin)
+{
+   if (!e->d_in)  { cudaError_t c = cudaMalloc(reinterpret_cast<void**>(&e->d_in), (size_t)e->win_cap + 64); if (c != cudaSuccess) return engine_fail(e, c, __FILE__, __LINE__); }
+   if (!e->d_out) { cudaError_t c = cudaMalloc(reinterpret_cast<void**>(&e->d_out), e->out_cap); if (c != cudaSuccess) return engine_fail(e, c, __FILE__, __LINE__); }
+   if (!e->h_out) { cudaError_t c = cudaMallocHost(reinterpret_cast<void**>(&e->h_out), e->out_cap); if (c != cudaSuccess) return engine_fail(e, c, __FILE__, __LINE__); }
+   if (need_hin && !e->h_in) { cudaError_t c = cudaMallocHost(reinterpret_cast<void**>(&e->h_in), (size_t)e->win_cap); if (c != cudaSuccess) return engine_fail(e, c, __FILE__, __LINE__); }
+   return 0;
+}
+
+static void stream_reset(EngineFull* e)
+{
+   memset(&e->ss, 0, sizeof e->ss);
+}
+
+// One window through all stages.  d_in: device input; writes coded blocks into d_out at
+// their absolute bit positions (relative to origin_bit) and advances ss.bits.
+static int run_window(EngineFull* e, const u8* d_in, u32 W, bool is_final, bool tail_merge,
+                      u8* d_out, u64 origin_bit, u32* consumed, u32* nb_out)
+{
+   cudaStream_t st = e->stream;
+   u32 nb = 0, cons = 0, E = 0;
+   StreamState& ss = e->ss;
+   cudaEventRecord(e->ev[0], st);
+   int rc = stage1_run(e, d_in, W, is_final, tail_merge, &nb, &cons, &E);
+   if (rc) { snprintf(g_err, sizeof g_err, "%s", e->err); return rc; }
+   cudaEventRecord(e->ev[1], st);
+   *consumed = cons; *nb_out = nb;
+   e->last_nb = nb; e->last_E = E;
+   if (nb == 0) return 0;
+   rc = stage2_run(e, nb, E);
+   if (rc) { snprintf(g_err, sizeof g_err, "%s", e->err); return rc; }
+   cudaEventRecord(e->ev[2], st);
+   rc = stage3_run(e, nb, E);
+   if (rc) { snprintf(g_err, sizeof g_err, "%s", e->err); return rc; }
+   cudaEventRecord(e->ev[3], st);
+   u64 end_bit = 0;
+   rc = stage4_run(e, nb, E, d_out, origin_bit, ss.bits, &end_bit);
+   if (rc) { snprintf(g_err, sizeof g_err, "%s", e->err); return rc; }
+   cudaEventRecord(e->ev[4], st);
+   // per-block results for the combined CRC and the statistics
+   BZ_CUDA(e, cudaMemcpyAsync(e->h_blk, e->bt.crc, sizeof(u32) * nb, cudaMemcpyDeviceToHost, st));
+   BZ_CUDA(e, cudaMemcpyAsync(e->h_blk + e->blk_cap, e->bt.nmtf, sizeof(u32) * nb, cudaMemcpyDeviceToHost, st));
+   BZ_CUDA(e, cudaMemcpyAsync(e->h_blk + 2 * (size_t)e->blk_cap, e->bt.power_q, sizeof(u32) * nb, cudaMemcpyDeviceToHost, st));
+   BZ_CUDA(e, cudaStreamSynchronize(st));
+   for (u32 b = 0; b < nb; b++) {
+      ss.combined_crc = ((ss.combined_crc << 1) | (ss.combined_crc >> 31)) ^ e->h_blk[b];
+      ss.st.sum_nmtf += e->h_blk[e->blk_cap + b];
+      if (e->h_blk[2 * (size_t)e->blk_cap + b]) ss.st.n_power_blocks++;
+   }
+   ss.block_no += nb;
+   ss.bits = end_bit;
+   ss.st.n_blocks += nb; ss.st.n_windows++; ss.st.sum_nblock += E;
+   float ms;
+   cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]); ss.st.ms_s1 += ms;
+   cudaEventElapsedTime(&ms, e->ev[1], e->ev[2]); ss.st.ms_s2 += ms;
+   cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]); ss.st.ms_s3 += ms;
+   cudaEventElapsedTime(&ms, e->ev[3], e->ev[4]); ss.st.ms_s4 += ms;
+   cudaEventElapsedTime(&ms, e->ev[0], e->ev[4]); ss.st.ms_total += ms;
+   return 0;
+}
+
+// ---- host-side bit carry helpers ----------------------------------------------------------
+struct Sink {
+   bz2b200_sink fn; void* user;
+   u8* dst; size_t cap, len;      // used when fn == nullptr
+   int put(const u8* p, size_t n)
+   {
+      if (fn) return fn(user, p, n);
+      if (len + n > cap) return BZ2B200_EOUTFULL;
+      memcpy(dst + len, p, n);
+      len += n;
+      return 0;
+   }
+};
+
+static int host_put_bits(EngineFull* e, Sink& sk, u64 value, int nbits)
+{
+   StreamState& ss = e->ss;
+   for (int k = nbits - 1; k >= 0; k--) {
+      ss.carry = (u8)(ss.carry | (((value >> k) & 1) << (7 - ss.ncarry)));
+      ss.ncarry++;
+      if (ss.ncarry == 8) { int rc = sk.put(&ss.carry, 1); if (rc) return rc; ss.carry = 0; ss.ncarry = 0; }
+   }
+   ss.bits += (u64)nbits;
+   return 0;
+}
+
+// Process one window whose input is already in device memory at d_in; compressed bytes go to the sink.
+static int window_to_sink(EngineFull* e, const u8* d_in, u32 W, bool is_final, bool tail_merge, Sink& sk, u32* consumed)
+{
+   StreamState& ss = e->ss;
+   cudaStream_t st = e->stream;
+   const u64 bits_before = ss.bits;
+   const u64 origin_bit = (bits_before >> 5) << 5;
+   BZ_CUDA(e, cudaMemsetAsync(e->d_out, 0, e->out_cap, st));
+   u32 nb = 0;
+   int rc = run_window(e, d_in, W, is_final, tail_merge, e->d_out, origin_bit, consumed, &nb);
+   if (rc) return rc;
+   if (nb == 0) return 0;
+   const u64 end_bit = ss.bits;
+   const size_t nbytes = (size_t)((end_bit - origin_bit + 7) >> 3);
+   if (nbytes > e->out_cap) return set_err(BZ2B200_EINTERNAL, "window output exceeds staging capacity");
+   BZ_CUDA(e, cudaMemcpyAsync(e->h_out, e->d_out, nbytes, cudaMemcpyDeviceToHost, st));
+   BZ_CUDA(e, cudaStreamSynchronize(st));
+   const size_t skip = (size_t)((bits_before >> 3) - (origin_bit >> 3));
+   const size_t full_end = (size_t)((end_bit >> 3) - (origin_bit >> 3));     // first byte that is not complete
+   if (ss.ncarry) e->h_out[skip] |= ss.carry;
+   if (full_end > skip) { rc = sk.put(e->h_out + skip, full_end - skip); if (rc) return rc; }
+   ss.ncarry = (u32)(end_bit & 7);
+   ss.carry = ss.ncarry ? e->h_out[full_end] : 0;
+   if (full_end == skip && (bits_before & 7)) { /* still inside the same partial byte */ }
+   return 0;
+}
+
+static int finish_stream(EngineFull* e, Sink& sk)
+{
+   StreamState& ss = e->ss;
+   int rc;
+   if ((rc = host_put_bits(e, sk, 0x177245385090ULL, 48))) return rc;     // compress.c:874-875
+   if ((rc = host_put_bits(e, sk, ss.combined_crc, 32))) return rc;       // :876
+   if (ss.ncarry) { rc = sk.put(&ss.carry, 1); if (rc) return rc; ss.bits += 8 - ss.ncarry; ss.carry = 0; ss.ncarry = 0; }   // :879
+   return 0;
+}
+
+static int begin_stream(EngineFull* e, Sink& sk)
+{
+   StreamState& ss = e->ss;
+   if (ss.header_done) return 0;
+   ss.header_done = true;
+   return host_put_bits(e, sk, 0x425A6830u + (u32)e->level, 32);            // compress.c:841-845  "BZh" '0'+level
+}
+
+} // namespace bz
+
+using namespace bz;
+
+extern "C" {
+
+const char* bz2b200_last_error(void) { return g_err; }
+const char* bz2b200_version(void) { return "bzip2-b200 0.1 (sm_100a), stream-compatible with libbzip2 1.0.6x"; }
+
+int bz2b200_device_count(void)
+{
+   int n = 0;
+   if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+   return n;
+}
+
+int bz2b200_engine_create(bz2b200_engine** out, int device, int block_size_100k, size_t window_bytes)
+{
+   if (!out) return set_err(BZ2B200_EPARAM, "null out pointer");
+   EngineFull* e = nullptr;
+   int rc = engine_new(&e, device, block_size_100k, window_bytes);
+   if (rc) return rc;
+   stream_reset(e);
+   *out = reinterpret_cast<bz2b200_engine*>(e);
+   return 0;
+}
+
+void bz2b200_engine_destroy(bz2b200_engine* h)
+{
+   engine_free(reinterpret_cast<EngineFull*>(h));
+}
+
+int bz2b200_compress_host(bz2b200_engine* h, const void* src, size_t src_len, void* dst, size_t* dst_len,
+                          unsigned flags, bz2b200_stats* stats)
+{
+   EngineFull* e = reinterpret_cast<EngineFull*>(h);
+   if (!e || !dst || !dst_len || (!src && src_len)) return set_err(BZ2B200_EPARAM, "bad argument");
+   cudaSetDevice(e->device);
+   int rc = ensure_staging(e, false);
+   if (rc) return rc;
+   stream_reset(e);
+   Sink sk; sk.fn = nullptr; sk.user = nullptr; sk.dst = static_cast<u8*>(dst); sk.cap = *dst_len; sk.len = 0;
+   if ((rc = begin_stream(e, sk))) return rc;
+   const u8* in = static_cast<const u8*>(src);
+   const bool tail_merge = !(flags & BZ2B200_TAIL_STREAMED);
+   size_t pos = 0;
+   while (pos < src_len) {
+      const size_t W = (src_len - pos < e->win_cap) ? (src_len - pos) : e->win_cap;
+      const bool fin = (pos + W == src_len);
+      BZ_CUDA(e, cudaMemcpyAsync(e->d_in, in + pos, W, cudaMemcpyHostToDevice, e->stream));
+      u32 cons = 0;
+      rc = window_to_sink(e, e->d_in, (u32)W, fin, tail_merge, sk, &cons);
+      if (rc) return rc;
+      if (cons == 0) return set_err(BZ2B200_EINTERNAL, "window made no progress");
+      pos += cons;
+   }
+   if ((rc = finish_stream(e, sk))) return rc;
+   *dst_len = sk.len;
+   e->ss.st.in_bytes = src_len; e->ss.st.out_bytes = sk.len; e->ss.st.combined_crc = e->ss.combined_crc;
+   if (stats) *stats = e->ss.st;
+   return 0;
+}
+
+int bz2b200_compress_device(bz2b200_engine* h, const void* d_src, size_t src_len, void* d_dst, size_t dst_cap,
+                            size_t* dst_len, unsigned flags, bz2b200_stats* stats)
+{
+   EngineFull* e = reinterpret_cast<EngineFull*>(h);
+   if (!e || !d_dst || !dst_len || (!d_src && src_len) || ((uintptr_t)d_dst & 3)) return set_err(BZ2B200_EPARAM, "bad argument");
+   cudaSetDevice(e->device);
+   stream_reset(e);
+   StreamState& ss = e->ss;
+   u8* out = static_cast<u8*>(d_dst);
+   // worst case: incompressible data grows by < 1% plus per-block tables
+   const size_t need = src_len + src_len / 64 + (src_len / e->nmax + 2) * 24576 + 64;
+   if (dst_cap < need) return set_err(BZ2B200_EOUTFULL, "device destination too small (need src_len*1.016 + 24 KiB per block)");
+   BZ_CUDA(e, cudaMemsetAsync(out, 0, dst_cap & ~(size_t)3, e->stream));
+   int rc = put_bits_device(e, out, 0, 0, 0x425A6830u + (u32)e->level, 32);
+   if (rc) return rc;
+   ss.bits = 32; ss.header_done = true;
+   const u8* in = static_cast<const u8*>(d_src);
+   const bool tail_merge = !(flags & BZ2B200_TAIL_STREAMED);
+   size_t pos = 0;
+   while (pos < src_len) {
+      const size_t W = (src_len - pos < e->win_cap) ? (src_len - pos) : e->win_cap;
+      const bool fin = (pos + W == src_len);
+      u32 cons = 0, nb = 0;
+      rc = run_window(e, in + pos, (u32)W, fin, tail_merge, out, 0, &cons, &nb);
+      if (rc) return rc;
+      if (cons == 0) return set_err(BZ2B200_EINTERNAL, "window made no progress");
+      pos += cons;
+   }
+   if ((rc = put_bits_device(e, out, 0, ss.bits, 0x177245385090ULL, 48))) return rc;
+   ss.bits += 48;
+   if ((rc = put_bits_device(e, out, 0, ss.bits, ss.combined_crc, 32))) return rc;
+   ss.bits += 32;
+   BZ_CUDA(e, cudaStreamSynchronize(e->stream));
+   *dst_len = (size_t)((ss.bits + 7) >> 3);
+   ss.st.in_bytes = src_len; ss.st.out_bytes = *dst_len; ss.st.combined_crc = ss.combined_crc;
+   if (stats) *stats = ss.st;
+   return 0;
+}
+
+int bz2b200_stream_begin(bz2b200_engine* h)
+{
+   EngineFull* e = reinterpret_cast<EngineFull*>(h);
+   if (!e) return set_err(BZ2B200_EPARAM, "null engine");
+   cudaSetDevice(e->device);
+   int rc = ensure_staging(e, true);
+   if (rc) return rc;
+   stream_reset(e);
+   return 0;
+}
+
+int bz2b200_stream_feed(bz2b200_engine* h, const void* src, size_t n, int end_mode, bz2b200_sink sink, void* user)
+{
+   EngineFull* e = reinterpret_cast<EngineFull*>(h);
+   if (!e || !sink || (!src && n) || end_mode < 0 || end_mode > 2) return set_err(BZ2B200_EPARAM, "bad argument");
+   if (!e->h_in) return set_err(BZ2B200_EPARAM, "bz2b200_stream_begin was not called");
+   cudaSetDevice(e->device);
+   StreamState& ss = e->ss;
+   Sink sk; sk.fn = sink; sk.user = user; sk.dst = nullptr; sk.cap = 0; sk.len = 0;
+   int rc;
+   if ((rc = begin_stream(e, sk))) return rc;
+   const u8* in = static_cast<const u8*>(src);
+   if (n) ss.tail_running = (end_mode == 0);
+   ss.st.in_bytes += n;
+   size_t off = 0;
+   for (;;) {
+      const size_t room = (size_t)e->win_cap - ss.h_fill;
+      const size_t take = (n - off < room) ? (n - off) : room;
+      if (take) { memcpy(e->h_in + ss.h_fill, in + off, take); ss.h_fill += take; off += take; }
+      const bool all_in = (off == n);
+      const bool closing = (end_mode != 0) && all_in;
+      if (ss.h_fill < e->win_cap && !closing) break;          // wait for more input
+      if (ss.h_fill == 0) break;
+      BZ_CUDA(e, cudaMemcpyAsync(e->d_in, e->h_in, ss.h_fill, cudaMemcpyHostToDevice, e->stream));
+      u32 cons = 0;
+      rc = window_to_sink(e, e->d_in, (u32)ss.h_fill, closing, closing && !ss.tail_running, sk, &cons);
+      if (rc) return rc;
+      if (cons == 0 && !closing) return set_err(BZ2B200_EINTERNAL, "window made no progress");
+      if (cons < ss.h_fill) memmove(e->h_in, e->h_in + cons, ss.h_fill - cons);
+      ss.h_fill -= cons;
+      if (all_in && ss.h_fill == 0) break;
+      if (all_in && !closing) break;
+   }
+   if (end_mode == 2) {
+      if ((rc = finish_stream(e, sk))) return rc;
+   }
+   return 0;
+}
+
+int bz2b200_debug_keep(bz2b200_engine* h, int on)
+{
+   EngineFull* e = reinterpret_cast<EngineFull*>(h);
+   if (!e) return BZ2B200_EPARAM;
+   e->debug_keep = on != 0;
+   return 0;
+}
+
+int bz2b200_debug_fetch(bz2b200_engine* h, const char* name, void* dst, size_t cap, size_t* got)
+{
+   EngineFull* e = reinterpret_cast<EngineFull*>(h);
+   if (!e || !name || !dst || !got) return set_err(BZ2B200_EPARAM, "bad argument");
+   cudaSetDevice(e->device);
+   const size_t nb = e->last_nb, E = e->last_E;
+   const void* src = nullptr; size_t bytes = 0;
+   struct { const char* n; const void* p; size_t b; } tab[] = {
+      {"X", e->bt.X, (nb + 1) * 4}, {"P", e->bt.P, (nb + 1) * 4}, {"crc", e->bt.crc, nb * 4},
+      {"origptr", e->bt.origptr, nb * 4}, {"power_q", e->bt.power_q, nb * 4}, {"inuse", e->bt.inuse, nb * 256},
+      {"ninuse", e->bt.ninuse, nb * 4}, {"nmtf", e->bt.nmtf, nb * 4}, {"mtffreq", e->bt.mtffreq, nb * BZ_MAX_ALPHA * 4},
+      {"bits", e->bt.bits, nb * 8}, {"bitoff", e->bt.bitoff, (nb + 1) * 8},
+      {"enc", e->enc, E}, {"bwt", e->bwt, E}, {"z", e->z, E}, {"mtfv", e->mtfv, (E + nb) * 2}, {"sa", e->sa, E * 4},
+      {"rank", e->rank, E * 4},
+      {"sel", e->sel, E / 50 + 2 * nb + 8}, {"hlen", e->hlen, nb * 6 * BZ_MAX_ALPHA}, {"ngroups", e->ngroups, nb * 4},
+      {"prebits", e->prebits, nb * 4},
+   };
+   for (auto& t : tab) if (!strcmp(t.n, name)) { src = t.p; bytes = t.b; }
+   if (!src) return set_err(BZ2B200_EPARAM, "unknown debug buffer name");
+   if (bytes > cap) return set_err(BZ2B200_EOUTFULL, "debug destination too small");
+   if (bytes) BZ_CUDA(e, cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+   *got = bytes;
+   return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,128 @@
+// engine.h -- internal C++ view of the compression engine (one per bz_stream / per GPU).
+//
+// A "window" is a slice of the input resident in HBM.  One window is cut into
+// bzip2 blocks by stage 1 and all of its complete blocks go through stages 2-5
+// together, so every kernel launch covers hundreds of blocks.
+//
+// HBM layout for a window (E = encoded bytes of the window, <= 1.25 * W):
+//   enc   u8 [E]    RLE1 output of the whole window; block b is enc[X[b], X[b+1])
+//   cend  u8 [E]    1 where an RLE1 chunk ends (block boundaries may only fall there)
+//   sa    u32[E]    per block: rotation start indices in sorted order (block-local)
+//   rank  u32[E]    per block: group-start rank of each rotation (block-local)
+//   nrank u32[E]    new ranks by sorted position (applied after each refinement round)
+//   keyA/keyB/idxB  u32[E] scratch for the large-segment radix path
+//   bwt   u8 [E]    last column;   z u8[E]  MTF positions;   mtfv u16[E + 2*nb]
+//   hist  u32[nb*65536]  bigram bucket histogram / cursors
+#pragma once
+#include "common.cuh"
+
+namespace bz {
+
+constexpr int N_SMALL_CLASSES = 5;          // segment lengths 2, 3-4, 5-8, 9-16, 17-32
+constexpr int CLS_MED1 = 5;                 // 33..512
+constexpr int CLS_MED2 = 6;                 // 513..4096
+constexpr int CLS_LARGE = 7;                // > 4096
+constexpr int N_CLASSES = 8;
+constexpr u32 MED1_MAX = 512;
+constexpr u32 MED2_MAX = 4096;
+constexpr u32 MAX_BLOCKS = 4096;            // block id must fit 12 bits in a segment entry
+constexpr u32 MAX_ENC = 1u << 27;           // flat position must fit 27 bits in a small entry
+
+constexpr int MTF_TILE = 1024;              // symbols per MTF tile (one warp each)
+
+// Segment worklists, double buffered.  Small classes hold u32 entries
+// (pos | (len-1) << 27); medium/large hold u64 entries (pos << 32 | blk << 20 | len).
+struct SegLists {
+   u32* small_items[2][N_SMALL_CLASSES];
+   u64* big_items[2][3];
+   u32* counts[2];                          // [N_CLASSES] each, device
+   u32  small_cap[N_SMALL_CLASSES];
+   u32  big_cap[3];
+};
+
+struct BlockTables {                        // per-window block metadata (device arrays, nb+1 or nb long)
+   u32* X;          // [nb+1] encoded start offset of each block
+   u32* P;          // [nb+1] input start offset of each block
+   u32* crc;        // [nb]   finalised block CRC
+   u32* origptr;    // [nb]
+   u32* power_q;    // [nb]   0, or q if the block is an exact power u^q
+   u8*  inuse;      // [nb*256]
+   u32* ninuse;     // [nb]
+   u32* nmtf;       // [nb]
+   i32* mtffreq;    // [nb*258]
+   u32* mtfbase;    // [nb]   start of block's symbols in mtfv (u16 units)
+   u64* bits;       // [nb]   total bits of the coded block (header + tables + payload)
+   u64* bitoff;     // [nb+1] absolute stream bit offset of each block
+};
+
+struct Engine;
+
+// ---- stage launchers (each returns 0 or a negative error; all work on e->stream) ----
+int stage1_run(Engine* e, const u8* d_in, u32 W, bool is_final, bool tail_merge, u32* nb_out, u32* consumed_out, u32* enc_total_out);
+int stage2_run(Engine* e, u32 nb, u32 E);
+int stage3_run(Engine* e, u32 nb, u32 E);
+int stage4_run(Engine* e, u32 nb, u32 E, u8* d_out, u64 origin_bit, u64 start_bit, u64* end_bit_out);
+int put_bits_device(Engine* e, u8* d_out, u64 origin_bit, u64 bitpos, u64 value, int nbits);
+
+struct Engine {
+   int device;
+   int level;
+   u32 nmax;               // 100000*level - 19   (bzlib.c:190)
+   cudaStream_t stream;
+   int num_sms;
+
+   // capacities
+   u32 win_cap;            // max input bytes per window
+   u32 enc_cap;            // max encoded bytes per window
+   u32 blk_cap;            // max blocks per window
+
+   // window buffers
+   u8  *enc, *cend;
+   u32 *sa, *rank, *nrank, *keyA, *keyB, *idxB;
+   u8  *bwt, *z;
+   u16 *mtfv;
+   u32 *hist;
+   u32 *blockmap;          // [enc_cap/4096 + 2] block id of each 4 KiB chunk of enc
+   SegLists lists;
+   BlockTables bt;
+
+   // stage-1 tile scratch
+   u32 *tile_len, *tile_ext, *tile_carry, *tile_size, *tile_base;
+   u32 *s1_scalars;        // [8]: nb, consumed, enc_total, ...
+
+   // stage-3 scratch
+   u8  *mtf_summary;       // [tiles*256] recency lists per tile, then start lists
+   u32 *mtf_tilemeta;      // [blk_cap*tiles_max*5] lead, trail, inner, out_base | carry
+   u32 *mtf_tilecnt;       // [blk_cap*tiles_max] distinct symbols per tile
+   // stage-4 scratch
+   u8  *sel;               // [E/50 + nb] selectors
+   u32 *selbase;           // [nb+1]
+   u8  *hlen;              // [nb*6*258] code lengths
+   i32 *hfreq;             // [nb*6*258] per-table frequencies
+   u32 *hcode;             // [nb*6*258]
+   u32 *grpbits;           // [nsel] bits per group, then exclusive offsets
+   u8  *pre;               // [nb*PRE_STRIDE] per-block preamble bits
+   u32 *prebits;           // [nb]
+   u32 *ngroups;           // [nb]
+
+   // device staging for the host API
+   u8  *d_in;              // [win_cap + 64]
+   u8  *d_out;             // [out_cap]
+   size_t out_cap;
+
+   // pinned host mirrors
+   u32 *h_scalars;         // [64]
+   u32 *h_counts;          // [N_CLASSES]
+   u32 *h_blk;             // [blk_cap*4] per-block results (crc, X, nmtf, power_q)
+   u8  *h_in;              // [win_cap] pinned staging for streamed input
+   u8  *h_out;             // [out_cap] pinned staging for compressed bytes
+
+   char err[256];
+};
+
+int engine_fail(Engine* e, cudaError_t c, const char* file, int line);
+
+#define BZ_CUDA(e, call) do { cudaError_t c_ = (call); if (c_ != cudaSuccess) return engine_fail((e), c_, __FILE__, __LINE__); } while (0)
+#define BZ_KCHECK(e) BZ_CUDA(e, cudaGetLastError())
+
+} // namespace bz

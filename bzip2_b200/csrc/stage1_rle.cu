@@ -1,0 +1,407 @@
+// stage1_rle.cu -- S1: initial run-length coding, block split and block CRCs.
+//
+// Replaces copy_input_until_stop (reference bzlib.c:211-315) and the per-byte
+// BZ_UPDATE_CRC (bzlib_private.h:197-202, crctable.c:29-99).
+//
+// The reference walks the input one byte at a time.  Restated for a parallel
+// machine: the input is a sequence of "chunks" (maximal runs cut every 255
+// bytes); a chunk of length L costs min(L,4) + (L>=4) encoded bytes; a block
+// closes at the first chunk end where its encoded size reaches nblockMAX.
+// Everything except that greedy chain is a scan:
+//   k_tile<AGG>      per 4 KiB tile: (trailing run length, tile-is-one-run) aggregate
+//   k_scan_runs      segmented scan of the aggregates -> run length entering each tile
+//   k_tile<COUNT>    encoded bytes produced by each tile
+//   k_scan_u32       exclusive scan -> encoded offset of each tile
+//   k_tile<SCATTER>  write enc[] and the chunk-end flags cend[]
+//   k_chain          one warp follows the greedy block chain through cend[]
+//   k_tile<FIND>     map each block's encoded start back to its input position
+//   k_crc            block CRCs: per-thread table CRC, GF(2) shift-combine, atomicXor
+#include "engine.h"
+
+namespace bz {
+
+constexpr int S1_THREADS = 256;
+constexpr int S1_BPT = 16;
+constexpr int S1_TILE = S1_THREADS * S1_BPT;   // 4096
+
+enum { S1_AGG = 0, S1_COUNT = 1, S1_SCATTER = 2, S1_FIND = 3 };
+
+struct RunAgg { u32 len; u32 ext; };   // ext: every position so far continues the run entering the range
+__device__ __forceinline__ RunAgg run_comb(RunAgg a, RunAgg b)
+{
+   RunAgg r;
+   r.len = b.ext ? a.len + b.len : b.len;
+   r.ext = a.ext & b.ext;
+   return r;
+}
+
+// Exclusive block scan of RunAgg (identity = {0,1}); also returns the block aggregate.
+__device__ __forceinline__ RunAgg run_block_excl(RunAgg v, RunAgg* wsm, RunAgg* total)
+{
+   const u32 l = lane_id(), w = threadIdx.x >> 5;
+   RunAgg inc = v;
+#pragma unroll
+   for (int d = 1; d < 32; d <<= 1) {
+      RunAgg t;
+      t.len = __shfl_up_sync(FULL, inc.len, d);
+      t.ext = __shfl_up_sync(FULL, inc.ext, d);
+      if (l >= (u32)d) inc = run_comb(t, inc);
+   }
+   __syncthreads();
+   if (l == 31) wsm[w] = inc;
+   __syncthreads();
+   RunAgg pre; pre.len = 0; pre.ext = 1;
+   for (u32 k = 0; k < w; k++) pre = run_comb(pre, wsm[k]);
+   RunAgg tot = pre;
+   for (u32 k = w; k < S1_THREADS / 32; k++) tot = run_comb(tot, wsm[k]);
+   if (total) *total = tot;
+   // exclusive within warp
+   RunAgg ex;
+   ex.len = __shfl_up_sync(FULL, inc.len, 1);
+   ex.ext = __shfl_up_sync(FULL, inc.ext, 1);
+   if (l == 0) { ex.len = 0; ex.ext = 1; }
+   return run_comb(pre, ex);
+}
+
+struct S1Params {
+   const u8* in;        // window base (any alignment)
+   u32 W;               // window length
+   u32 is_final;
+   u32* tile_len; u32* tile_ext; u32* tile_carry; u32* tile_size; u32* tile_base;
+   u8* enc; u8* cend;
+   const u32* X; u32* P; u32 nb_find;   // FIND mode
+   const u32* scalars;                   // [2] = enc_total
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(S1_THREADS) k_tile(S1Params p)
+{
+   __shared__ RunAgg wsm[S1_THREADS / 32];
+   __shared__ u32 ssm[34];
+   __shared__ u32 s_tile;
+   const u32 align = (u32)((uintptr_t)p.in & 15);
+   const u8* base = p.in - align;
+   u32 tile = blockIdx.x;
+   u32 findX = 0;
+   if (MODE == S1_FIND) {
+      // one CTA per boundary: locate the tile whose encoded range contains X[b]
+      const u32 b = blockIdx.x + 1;
+      findX = p.X[b];
+      const u32 ntiles = (p.W + align + S1_TILE - 1) / S1_TILE;
+      if (findX >= p.scalars[2]) { if (threadIdx.x == 0) p.P[b] = p.W; return; }
+      if (threadIdx.x == 0) {
+         u32 lo = 0, hi = ntiles - 1;          // largest t with tile_base[t] <= X and tile non-empty beyond
+         while (lo < hi) {
+            u32 mid = (lo + hi + 1) >> 1;
+            if (p.tile_base[mid] <= findX) lo = mid; else hi = mid - 1;
+         }
+         // step back over empty tiles that share the same base
+         while (lo > 0 && p.tile_size[lo] == 0) lo--;
+         s_tile = lo;
+      }
+      __syncthreads();
+      tile = s_tile;
+   }
+   const i64 pos0 = (i64)tile * S1_TILE + (i64)threadIdx.x * S1_BPT - (i64)align;   // window position of c[0]
+   u8 c[S1_BPT];
+   {
+      const u8* src = base + (size_t)tile * S1_TILE + (size_t)threadIdx.x * S1_BPT;
+      if (pos0 >= 0 && pos0 + S1_BPT <= (i64)p.W) {
+         uint4 v = *reinterpret_cast<const uint4*>(src);
+         u32 w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+         for (int k = 0; k < 16; k++) c[k] = (u8)(w4[k >> 2] >> ((k & 3) * 8));
+      } else {
+#pragma unroll
+         for (int k = 0; k < 16; k++) { i64 q = pos0 + k; c[k] = (q >= 0 && q < (i64)p.W) ? src[k] : 0; }
+      }
+   }
+   u32 prevb = 256, nextb = 256;
+   if (pos0 >= 1 && pos0 - 1 < (i64)p.W) prevb = p.in[pos0 - 1];
+   if (pos0 + S1_BPT >= 0 && pos0 + S1_BPT < (i64)p.W) nextb = p.in[pos0 + S1_BPT];
+
+   // per-position "continues the run" flags and the thread aggregate
+   u32 eqmask = 0, vmask = 0;
+   RunAgg agg; agg.len = 0; agg.ext = 1;
+#pragma unroll
+   for (int k = 0; k < 16; k++) {
+      i64 q = pos0 + k;
+      bool valid = (q >= 0 && q < (i64)p.W);
+      u32 pb = (k == 0) ? prevb : (u32)c[k - 1];
+      if (k > 0 && q == 0) pb = 256;                       // window position 0 never continues a run
+      bool eq = valid && (pb == (u32)c[k]);
+      if (valid) {
+         vmask |= 1u << k;
+         if (eq) { eqmask |= 1u << k; agg.len += 1; } else { agg.len = 1; agg.ext = 0; }
+      }
+   }
+   RunAgg tot;
+   RunAgg pre = run_block_excl(agg, wsm, &tot);
+   if (MODE == S1_AGG) {
+      if (threadIdx.x == 0) { p.tile_len[tile] = tot.len; p.tile_ext[tile] = tot.ext; }
+      return;
+   }
+   const u32 carry = p.tile_carry[tile];
+   u32 rbefore = pre.ext ? carry + pre.len : pre.len;      // run length ending just before c[0]
+
+   // phases and emitted byte counts
+   u32 j = 0;                                               // phase of current position
+   u32 emitted = 0;
+   u32 ph[16];
+#pragma unroll
+   for (int k = 0; k < 16; k++) {
+      if (!((vmask >> k) & 1)) { ph[k] = 0xffff; continue; }
+      if ((eqmask >> k) & 1) {
+         if (k == 0) j = rbefore % 255u; else { j = j + 1; if (j == 255) j = 0; }
+      } else j = 0;
+      // careful: when k>0 and previous position was invalid (before window) j restarts at 0 via eq=false
+      ph[k] = j;
+      emitted += (j < 3) ? 1u : (j == 3 ? 2u : 0u);
+   }
+   u32 ttotal;
+   u32 off = block_excl_sum<S1_THREADS>(emitted, ssm, &ttotal);
+   if (MODE == S1_COUNT) {
+      if (threadIdx.x == 0) p.tile_size[tile] = ttotal;
+      return;
+   }
+   u32 E = p.tile_base[tile] + off;
+#pragma unroll
+   for (int k = 0; k < 16; k++) {
+      if (ph[k] == 0xffff) continue;
+      const u32 jj = ph[k];
+      const i64 q = pos0 + k;
+      const u32 ch = c[k];
+      const u32 nb_ = (k == 15) ? nextb : (((vmask >> (k + 1)) & 1) ? (u32)c[k + 1] : 256u);
+      bool last = (jj == 254);
+      if (q == (i64)p.W - 1) last = last || (p.is_final != 0);
+      else last = last || (nb_ != ch);
+      if (MODE == S1_FIND) {
+         if (jj == 0 && E == findX) p.P[blockIdx.x + 1] = (u32)q;
+         E += (jj < 3) ? 1u : (jj == 3 ? 2u : 0u);
+         continue;
+      }
+      if (jj < 3) {
+         p.enc[E] = (u8)ch;
+         if (last) p.cend[E] = 1;
+         E += 1;
+      } else if (jj == 3) {
+         p.enc[E] = (u8)ch;
+         if (last) { p.enc[E + 1] = 0; p.cend[E + 1] = 1; }
+         E += 2;
+      } else {
+         if (last) { p.enc[E - 1] = (u8)(jj - 3); p.cend[E - 1] = 1; }
+      }
+   }
+}
+
+// Segmented scan of tile aggregates: carry[t] = run length ending just before tile t.
+__global__ void __launch_bounds__(1024) k_scan_runs(const u32* tile_len, const u32* tile_ext, u32* carry, u32 ntiles)
+{
+   __shared__ RunAgg wsm[32];
+   __shared__ RunAgg s_run;
+   if (threadIdx.x == 0) { s_run.len = 0; s_run.ext = 1; }
+   __syncthreads();
+   const u32 l = lane_id(), w = threadIdx.x >> 5;
+   for (u32 base = 0; base < ntiles; base += 1024) {
+      u32 t = base + threadIdx.x;
+      RunAgg v; v.len = 0; v.ext = 1;
+      if (t < ntiles) { v.len = tile_len[t]; v.ext = tile_ext[t]; }
+      RunAgg inc = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+         RunAgg q;
+         q.len = __shfl_up_sync(FULL, inc.len, d);
+         q.ext = __shfl_up_sync(FULL, inc.ext, d);
+         if (l >= (u32)d) inc = run_comb(q, inc);
+      }
+      if (l == 31) wsm[w] = inc;
+      __syncthreads();
+      RunAgg pre = s_run;
+      for (u32 k = 0; k < w; k++) pre = run_comb(pre, wsm[k]);
+      RunAgg ex;
+      ex.len = __shfl_up_sync(FULL, inc.len, 1);
+      ex.ext = __shfl_up_sync(FULL, inc.ext, 1);
+      if (l == 0) { ex.len = 0; ex.ext = 1; }
+      RunAgg mine = run_comb(pre, ex);            // aggregate of everything before tile t
+      if (t < ntiles) carry[t] = mine.len;        // valid as "run ending before t" because position-level len counts the trailing run
+      __syncthreads();
+      if (threadIdx.x == 1023) s_run = run_comb(pre, inc);
+      __syncthreads();
+   }
+}
+
+// Exclusive scan of a u32 array by one CTA; total -> *total_out.
+__global__ void __launch_bounds__(1024) k_scan_u32(const u32* in, u32* out, u32 n, u32* total_out)
+{
+   __shared__ u32 ssm[34];
+   __shared__ u32 s_run;
+   if (threadIdx.x == 0) s_run = 0;
+   __syncthreads();
+   for (u32 base = 0; base < n; base += 1024) {
+      u32 t = base + threadIdx.x;
+      u32 v = (t < n) ? in[t] : 0;
+      u32 tot;
+      u32 ex = block_excl_sum<1024>(v, ssm, &tot);
+      if (t < n) out[t] = s_run + ex;
+      __syncthreads();
+      if (threadIdx.x == 0) s_run += tot;
+      __syncthreads();
+   }
+   if (threadIdx.x == 0 && total_out) *total_out = s_run;
+}
+
+// Greedy block chain (bzlib.c:227 loop condition + :383): one warp.
+// scalars: [0]=nb  [1]=enc_used (X[nb])  [2]=enc_total (in)
+__global__ void k_chain(const u8* cend, u32* X, u32* scalars, u32 nmax, u32 is_final, u32 tail_merge, u32 blk_cap)
+{
+   const u32 l = lane_id();
+   const u32 Etot = scalars[2];
+   u32 x = 0, nb = 0;
+   if (l == 0) X[0] = 0;
+   while (x < Etot && nb < blk_cap) {
+      u32 target = x + nmax - 1;
+      if (target >= Etot) {
+         if (is_final) { nb++; if (l == 0) X[nb] = Etot; x = Etot; }
+         break;
+      }
+      u32 e = target + l;
+      bool f = (l < 8) && (e < Etot) && (cend[e] != 0);
+      u32 m = __ballot_sync(FULL, f);
+      if (m == 0) {
+         if (is_final) { nb++; if (l == 0) X[nb] = Etot; x = Etot; }
+         break;
+      }
+      u32 nx = target + (u32)(__ffs(m) - 1) + 1;
+      if (is_final && tail_merge && Etot - nx == 1) nx = Etot;
+      nb++;
+      if (l == 0) X[nb] = nx;
+      x = nx;
+   }
+   if (l == 0) { scalars[0] = nb; scalars[1] = x; }
+}
+
+// ---- CRC ------------------------------------------------------------------
+__device__ __forceinline__ u32 gf_mulmod(u32 a, u32 b)
+{
+   // (a * b) mod P over GF(2), P = x^32 + 0x04C11DB7; polynomials MSB = highest degree
+   u32 r = 0;
+#pragma unroll 4
+   for (int i = 31; i >= 0; i--) {
+      r = (r << 1) ^ ((r & 0x80000000u) ? 0x04C11DB7u : 0u);
+      if ((b >> i) & 1) r ^= a;
+   }
+   return r;
+}
+// x^(8*m) mod P by square-and-multiply over the precomputed table pw[k] = x^(8*2^k)
+__device__ __forceinline__ u32 gf_xpow8(const u32* pw, u64 m)
+{
+   u32 r = 1;                                    // the polynomial "1"
+   bool first = true;
+   for (int k = 0; m; k++, m >>= 1) {
+      if (m & 1) { r = first ? pw[k] : gf_mulmod(r, pw[k]); first = false; }
+   }
+   return r;
+}
+
+constexpr int CRC_THREADS = 256;
+constexpr int CRC_CTAS_PER_BLOCK = 64;
+
+__global__ void __launch_bounds__(CRC_THREADS) k_crc(const u8* in, const u32* P, u32* crc_acc)
+{
+   __shared__ u32 tab[256];
+   __shared__ u32 pw[40];
+   __shared__ u32 red[CRC_THREADS];
+   {
+      u32 r = threadIdx.x << 24;
+#pragma unroll
+      for (int k = 0; k < 8; k++) r = (r & 0x80000000u) ? (r << 1) ^ 0x04C11DB7u : (r << 1);
+      tab[threadIdx.x] = r;
+   }
+   if (threadIdx.x == 0) {
+      u32 v = 0x100;                              // x^8
+      // x^8 as a degree-<32 polynomial is the value 1<<8
+      for (int k = 0; k < 40; k++) { pw[k] = v; v = gf_mulmod(v, v); }
+   }
+   __syncthreads();
+   const u32 b = blockIdx.y;
+   const u64 lo_b = P[b], hi_b = P[b + 1];
+   const u64 L = hi_b - lo_b;
+   const u64 per_cta = (L + CRC_CTAS_PER_BLOCK - 1) / CRC_CTAS_PER_BLOCK;
+   const u64 lo = lo_b + per_cta * blockIdx.x;
+   u64 hi = lo + per_cta; if (hi > hi_b) hi = hi_b;
+   if (lo >= hi_b) return;
+   // right-aligned pieces of size s
+   const u64 len = hi - lo;
+   const u64 s = (len + CRC_THREADS - 1) / CRC_THREADS;
+   const i64 pe = (i64)hi - (i64)(CRC_THREADS - 1 - threadIdx.x) * (i64)s;   // piece end
+   i64 ps = pe - (i64)s;                                                      // piece start
+   if (ps < (i64)lo) ps = (i64)lo;
+   u32 c = 0;
+   for (i64 q = ps; q < pe; q++) c = (c << 8) ^ tab[(c >> 24) ^ in[q]];
+   red[threadIdx.x] = c;
+   __syncthreads();
+   // tree combine: v[t] = v[t] * x^(8*s*2^k) ^ v[t + 2^k]
+   u32 mult = gf_xpow8(pw, s);
+   for (int st = 1; st < CRC_THREADS; st <<= 1) {
+      if ((threadIdx.x & (2 * st - 1)) == 0) {
+         u32 a = red[threadIdx.x], bb = red[threadIdx.x + st];
+         red[threadIdx.x] = gf_mulmod(a, mult) ^ bb;
+      }
+      mult = gf_mulmod(mult, mult);
+      __syncthreads();
+   }
+   if (threadIdx.x == 0) {
+      u32 v = red[0];
+      u64 after = hi_b - hi;
+      if (after) v = gf_mulmod(v, gf_xpow8(pw, after));
+      if (blockIdx.x == 0) v ^= gf_mulmod(0xFFFFFFFFu, gf_xpow8(pw, L));   // the init value shifted through L bytes
+      atomicXor(&crc_acc[b], v);
+   }
+}
+
+__global__ void k_crc_final(u32* crc, u32 nb)
+{
+   u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+   if (b < nb) crc[b] = ~crc[b];
+}
+
+int stage1_run(Engine* e, const u8* d_in, u32 W, bool is_final, bool tail_merge,
+               u32* nb_out, u32* consumed_out, u32* enc_total_out)
+{
+   cudaStream_t st = e->stream;
+   const u32 align = (u32)((uintptr_t)d_in & 15);
+   const u32 ntiles = (W + align + S1_TILE - 1) / S1_TILE;
+   S1Params p;
+   p.in = d_in; p.W = W; p.is_final = is_final ? 1 : 0;
+   p.tile_len = e->tile_len; p.tile_ext = e->tile_ext; p.tile_carry = e->tile_carry;
+   p.tile_size = e->tile_size; p.tile_base = e->tile_base;
+   p.enc = e->enc; p.cend = e->cend; p.X = e->bt.X; p.P = e->bt.P; p.nb_find = 0; p.scalars = e->s1_scalars;
+
+   k_tile<S1_AGG><<<ntiles, S1_THREADS, 0, st>>>(p);                                   BZ_KCHECK(e);
+   k_scan_runs<<<1, 1024, 0, st>>>(e->tile_len, e->tile_ext, e->tile_carry, ntiles);   BZ_KCHECK(e);
+   k_tile<S1_COUNT><<<ntiles, S1_THREADS, 0, st>>>(p);                                 BZ_KCHECK(e);
+   k_scan_u32<<<1, 1024, 0, st>>>(e->tile_size, e->tile_base, ntiles, e->s1_scalars + 2); BZ_KCHECK(e);
+   BZ_CUDA(e, cudaMemcpyAsync(e->h_scalars, e->s1_scalars, 4 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+   BZ_CUDA(e, cudaStreamSynchronize(st));
+   const u32 Etot = e->h_scalars[2];
+   if (Etot > e->enc_cap) { snprintf(e->err, sizeof e->err, "encoded window %u exceeds capacity %u", Etot, e->enc_cap); return -3; }
+   BZ_CUDA(e, cudaMemsetAsync(e->cend, 0, (size_t)Etot + 16, st));
+   k_tile<S1_SCATTER><<<ntiles, S1_THREADS, 0, st>>>(p);                               BZ_KCHECK(e);
+   k_chain<<<1, 32, 0, st>>>(e->cend, e->bt.X, e->s1_scalars, e->nmax, is_final ? 1 : 0, tail_merge ? 1 : 0, e->blk_cap); BZ_KCHECK(e);
+   BZ_CUDA(e, cudaMemcpyAsync(e->h_scalars, e->s1_scalars, 4 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+   BZ_CUDA(e, cudaStreamSynchronize(st));
+   const u32 nb = e->h_scalars[0];
+   *nb_out = nb; *enc_total_out = e->h_scalars[1];
+   if (nb == 0) { *consumed_out = 0; return 0; }
+   BZ_CUDA(e, cudaMemsetAsync(e->bt.P, 0, sizeof(u32), st));
+   k_tile<S1_FIND><<<nb, S1_THREADS, 0, st>>>(p);                                      BZ_KCHECK(e);
+   BZ_CUDA(e, cudaMemsetAsync(e->bt.crc, 0, sizeof(u32) * nb, st));
+   k_crc<<<dim3(CRC_CTAS_PER_BLOCK, nb), CRC_THREADS, 0, st>>>(d_in, e->bt.P, e->bt.crc); BZ_KCHECK(e);
+   k_crc_final<<<(nb + 255) / 256, 256, 0, st>>>(e->bt.crc, nb);                        BZ_KCHECK(e);
+   BZ_CUDA(e, cudaMemcpyAsync(e->h_scalars + 8, e->bt.P + nb, sizeof(u32), cudaMemcpyDeviceToHost, st));
+   BZ_CUDA(e, cudaStreamSynchronize(st));
+   *consumed_out = e->h_scalars[8];
+   return 0;
+}
+
+} // namespace bz

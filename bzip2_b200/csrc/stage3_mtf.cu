@@ -1,0 +1,282 @@
+// stage3_mtf.cu -- S3: move-to-front + zero-run (RUNA/RUNB) coding of the BWT output.
+//
+// Replaces generateMTFValues (reference compress.c:93-229).  The reference is a serial
+// recurrence over the block; here the block is cut into tiles of MTF_TILE symbols:
+//   k_mtf_summary  (warp/tile)  distinct symbols of the tile, most recent first.  The
+//                               effect of a tile on the MTF list is "move these to the
+//                               front in this order", which composes left to right.
+//   k_mtf_lists    (CTA/block)  folds the summaries, storing the list each tile starts with
+//   k_mtf_encode   (warp/tile)  the real MTF: the list lives in registers (8 bytes per
+//                               lane); a symbol is located with a SWAR byte compare and a
+//                               ballot, and rotated to the front with one shuffle.
+//   k_rle2_count / k_rle2_scan / k_rle2_emit
+//                               zero runs are counted per tile, runs crossing tiles are
+//                               stitched by a per-block scan, then symbols are written at
+//                               their final offsets and mtfFreq is accumulated.
+// Output per block: mtfv[] (u16), nMTF, mtfFreq[258]; symbol values as in the reference
+// (RUNA=0, RUNB=1, position p>0 -> p+1, EOB = nInUse+1).
+#include "engine.h"
+
+namespace bz {
+
+struct S3Params {
+   const u8* bwt;
+   const u32* X;
+   const u8* inuse;
+   const u32* ninuse;
+   u8* lists;          // [nb * tiles_max * 256]
+   u32* tilecnt;       // [nb * tiles_max]
+   u32* tmeta;         // [nb * tiles_max * 4]: lead, trail|allzero<<31, inner, out_base
+   u32* tcarry;        // [nb * tiles_max]
+   u8* z;
+   u16* mtfv;
+   u32* nmtf;
+   i32* mtffreq;
+   u32 tiles_max;
+};
+
+__global__ void __launch_bounds__(256) k_mtf_summary(S3Params p)
+{
+   __shared__ u32 seen[8][8];
+   const u32 w = threadIdx.x >> 5, l = lane_id();
+   const u32 b = blockIdx.y;
+   const u32 t = blockIdx.x * 8 + w;
+   const u32 xb = p.X[b], n = p.X[b + 1] - xb;
+   if ((u64)t * MTF_TILE >= n) return;
+   const u32 start = xb + t * MTF_TILE;
+   const u32 size = min((u32)MTF_TILE, n - t * MTF_TILE);
+   const u32 nu = p.ninuse[b];
+   if (l < 8) seen[w][l] = 0;
+   __syncwarp();
+   u8* out = p.lists + ((size_t)b * p.tiles_max + t) * 256;
+   u32 count = 0;
+   for (u32 off = size; off > 0 && count < nu; off = (off > 32) ? off - 32 : 0) {
+      const bool valid = off > l;
+      const u32 s = valid ? p.bwt[start + off - 1 - l] : (0x100u + l);
+      const u32 m = __match_any_sync(FULL, s);
+      const bool first = (l == (u32)(__ffs(m) - 1));
+      const bool fresh = valid && first && !((seen[w][(s >> 5) & 7] >> (s & 31)) & 1u);
+      const u32 bal = __ballot_sync(FULL, fresh);
+      __syncwarp();
+      if (fresh) {
+         out[count + __popc(bal & lanemask_lt())] = (u8)s;
+         atomicOr(&seen[w][s >> 5], 1u << (s & 31));
+      }
+      count += __popc(bal);
+      __syncwarp();
+   }
+   if (l == 0) p.tilecnt[(size_t)b * p.tiles_max + t] = count;
+}
+
+__global__ void __launch_bounds__(256) k_mtf_lists(S3Params p)
+{
+   __shared__ u8 cur[2][256];
+   __shared__ u8 inset[256];
+   __shared__ u32 wcnt[8];
+   const u32 b = blockIdx.x;
+   const u32 tid = threadIdx.x, w = tid >> 5, l = lane_id();
+   const u32 n = p.X[b + 1] - p.X[b];
+   const u32 ntile = (n + MTF_TILE - 1) / MTF_TILE;
+   cur[0][tid] = 0; cur[1][tid] = 0;
+   const bool used = p.inuse[(size_t)b * 256 + tid] != 0;
+   {
+      const u32 bal = __ballot_sync(FULL, used);
+      if (l == 0) wcnt[w] = __popc(bal);
+      __syncthreads();
+      u32 base = 0;
+      for (u32 k = 0; k < w; k++) base += wcnt[k];
+      if (used) cur[0][base + __popc(bal & lanemask_lt())] = (u8)tid;
+   }
+   const u32 nu = p.ninuse[b];
+   __syncthreads();
+   u8* slot = p.lists + (size_t)b * p.tiles_max * 256;
+   const u32* tc = p.tilecnt + (size_t)b * p.tiles_max;
+   int sel = 0;
+   u8 pre_sym = slot[tid];
+   u32 pre_cnt = tc[0];
+   for (u32 t = 0; t < ntile; t++) {
+      const u8 s = pre_sym;
+      const u32 cnt = pre_cnt;
+      if (t + 1 < ntile) { pre_sym = slot[(size_t)(t + 1) * 256 + tid]; pre_cnt = tc[t + 1]; }
+      const u8 c = cur[sel][tid];
+      slot[(size_t)t * 256 + tid] = c;
+      inset[tid] = 0;
+      __syncthreads();
+      if (tid < cnt) inset[s] = 1;
+      __syncthreads();
+      const bool keep = (tid < nu) && !inset[c];
+      const u32 bal = __ballot_sync(FULL, keep);
+      if (l == 0) wcnt[w] = __popc(bal);
+      __syncthreads();
+      u32 base = cnt;
+      for (u32 k = 0; k < w; k++) base += wcnt[k];
+      if (keep) cur[sel ^ 1][base + __popc(bal & lanemask_lt())] = c;
+      if (tid < cnt) cur[sel ^ 1][tid] = s;
+      __syncthreads();
+      sel ^= 1;
+   }
+}
+
+__global__ void __launch_bounds__(256) k_mtf_encode(S3Params p)
+{
+   const u32 w = threadIdx.x >> 5, l = lane_id();
+   const u32 b = blockIdx.y;
+   const u32 t = blockIdx.x * 8 + w;
+   const u32 xb = p.X[b], n = p.X[b + 1] - xb;
+   if ((u64)t * MTF_TILE >= n) return;
+   const u32 start = xb + t * MTF_TILE;
+   const u32 size = min((u32)MTF_TILE, n - t * MTF_TILE);
+   u64 L = reinterpret_cast<const u64*>(p.lists + ((size_t)b * p.tiles_max + t) * 256)[l];
+   u32 front = __shfl_sync(FULL, (u32)(L & 0xff), 0);
+   for (u32 base = 0; base < size; base += 32) {
+      const u32 i = base + l;
+      const u32 sym = (i < size) ? p.bwt[start + i] : 0;
+      const u32 cntj = min(32u, size - base);
+      u32 myz = 0;
+      for (u32 j = 0; j < cntj; j++) {
+         const u32 c = __shfl_sync(FULL, sym, j);
+         u32 pos = 0;
+         if (c != front) {
+            const u64 x = L ^ (0x0101010101010101ULL * (u64)c);
+            const u64 zm = (x - 0x0101010101010101ULL) & ~x & 0x8080808080808080ULL;
+            const u32 hit = __ballot_sync(FULL, zm != 0);
+            if (hit) {
+               const u32 f = __ffs(hit) - 1;
+               u32 bi = zm ? (u32)((__ffsll((long long)zm) - 1) >> 3) : 0;
+               bi = __shfl_sync(FULL, bi, f);
+               pos = f * 8 + bi;
+               u32 top = __shfl_up_sync(FULL, (u32)(L >> 56), 1);
+               if (l == 0) top = c;
+               if (l < f) L = (L << 8) | (u64)top;
+               else if (l == f) {
+                  const u64 lowmask = bi ? ((1ULL << (8 * bi)) - 1ULL) : 0ULL;
+                  const u64 keepmask = (bi == 7) ? 0ULL : ~((1ULL << (8 * (bi + 1))) - 1ULL);
+                  L = (L & keepmask) | ((L & lowmask) << 8) | (u64)top;
+               }
+               front = c;
+            }
+         }
+         if (l == j) myz = pos;
+      }
+      if (i < size) p.z[start + i] = (u8)myz;
+   }
+}
+
+__device__ __forceinline__ u32 run_digits(u32 r) { return 31 - __clz(r + 1); }
+
+// one thread per tile: zero-run shape of the tile
+__global__ void __launch_bounds__(128) k_rle2_count(S3Params p)
+{
+   const u32 b = blockIdx.y;
+   const u32 t = blockIdx.x * 128 + threadIdx.x;
+   const u32 xb = p.X[b], n = p.X[b + 1] - xb;
+   if ((u64)t * MTF_TILE >= n) return;
+   const u32 start = xb + t * MTF_TILE;
+   const u32 size = min((u32)MTF_TILE, n - t * MTF_TILE);
+   u32 lead = 0, run = 0, inner = 0;
+   bool seen_nz = false;
+   for (u32 i = 0; i < size; i++) {
+      const u32 v = p.z[start + i];
+      if (v == 0) run++;
+      else {
+         if (!seen_nz) { lead = run; seen_nz = true; }
+         else if (run) inner += run_digits(run);
+         inner += 1;
+         run = 0;
+      }
+   }
+   u32* m = p.tmeta + ((size_t)b * p.tiles_max + t) * 4;
+   if (!seen_nz) { m[0] = size; m[1] = size | 0x80000000u; m[2] = 0; }
+   else { m[0] = lead; m[1] = run; m[2] = inner; }
+}
+
+// one thread per block: stitch runs across tiles, assign output offsets, nMTF
+__global__ void k_rle2_scan(S3Params p, u32 nb)
+{
+   const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+   if (b >= nb) return;
+   const u32 n = p.X[b + 1] - p.X[b];
+   const u32 ntile = (n + MTF_TILE - 1) / MTF_TILE;
+   u32* m = p.tmeta + (size_t)b * p.tiles_max * 4;
+   u32* cy = p.tcarry + (size_t)b * p.tiles_max;
+   u32 carry = 0, o = 0;
+   for (u32 t = 0; t < ntile; t++) {
+      cy[t] = carry;
+      m[4 * t + 3] = o;
+      const u32 trail = m[4 * t + 1];
+      if (trail & 0x80000000u) carry += (trail & 0x7fffffffu);
+      else {
+         const u32 r = carry + m[4 * t];
+         o += m[4 * t + 2] + (r ? run_digits(r) : 0);
+         carry = trail;
+      }
+   }
+   if (carry) o += run_digits(carry);
+   p.nmtf[b] = o + 1;                       // + EOB
+}
+
+__global__ void __launch_bounds__(128) k_rle2_emit(S3Params p)
+{
+   __shared__ u32 hist[BZ_MAX_ALPHA + 6];
+   const u32 b = blockIdx.y;
+   const u32 t = blockIdx.x * 128 + threadIdx.x;
+   const u32 xb = p.X[b], n = p.X[b + 1] - xb;
+   for (u32 k = threadIdx.x; k < BZ_MAX_ALPHA; k += 128) hist[k] = 0;
+   __syncthreads();
+   const u32 ntile = (n + MTF_TILE - 1) / MTF_TILE;
+   if (t < ntile) {
+      const u32 start = xb + t * MTF_TILE;
+      const u32 size = min((u32)MTF_TILE, n - t * MTF_TILE);
+      const u32* m = p.tmeta + ((size_t)b * p.tiles_max + t) * 4;
+      u16* out = p.mtfv + (size_t)xb + b + m[3];
+      u32 run = p.tcarry[(size_t)b * p.tiles_max + t];
+      u32 o = 0;
+      for (u32 i = 0; i < size; i++) {
+         const u32 v = p.z[start + i];
+         if (v == 0) { run++; continue; }
+         if (run) {
+            u32 zz = run - 1;
+            for (;;) { const u32 s = zz & 1; out[o++] = (u16)s; atomicAdd(&hist[s], 1u); if (zz < 2) break; zz = (zz - 2) >> 1; }
+            run = 0;
+         }
+         out[o++] = (u16)(v + 1);
+         atomicAdd(&hist[v + 1], 1u);
+      }
+      if (t == ntile - 1) {
+         if (run) {
+            u32 zz = run - 1;
+            for (;;) { const u32 s = zz & 1; out[o++] = (u16)s; atomicAdd(&hist[s], 1u); if (zz < 2) break; zz = (zz - 2) >> 1; }
+         }
+         const u32 eob = p.ninuse[b] + 1;
+         out[o++] = (u16)eob;
+         atomicAdd(&hist[eob], 1u);
+      }
+   }
+   __syncthreads();
+   for (u32 k = threadIdx.x; k < BZ_MAX_ALPHA; k += 128)
+      if (hist[k]) atomicAdd(&p.mtffreq[(size_t)b * BZ_MAX_ALPHA + k], (i32)hist[k]);
+}
+
+int stage3_run(Engine* e, u32 nb, u32 E)
+{
+   (void)E;
+   cudaStream_t st = e->stream;
+   const u32 tiles_max = (e->nmax + 16 + MTF_TILE - 1) / MTF_TILE;
+   S3Params p;
+   p.bwt = e->bwt; p.X = e->bt.X; p.inuse = e->bt.inuse; p.ninuse = e->bt.ninuse;
+   p.lists = e->mtf_summary; p.tilecnt = e->mtf_tilecnt; p.tmeta = e->mtf_tilemeta;
+   p.tcarry = e->mtf_tilemeta + (size_t)e->blk_cap * tiles_max * 4;
+   p.z = e->z; p.mtfv = e->mtfv; p.nmtf = e->bt.nmtf; p.mtffreq = e->bt.mtffreq; p.tiles_max = tiles_max;
+   BZ_CUDA(e, cudaMemsetAsync(e->bt.mtffreq, 0, sizeof(i32) * BZ_MAX_ALPHA * nb, st));
+   const dim3 gw((tiles_max + 7) / 8, nb);
+   const dim3 gt((tiles_max + 127) / 128, nb);
+   k_mtf_summary<<<gw, 256, 0, st>>>(p);                BZ_KCHECK(e);
+   k_mtf_lists<<<nb, 256, 0, st>>>(p);                  BZ_KCHECK(e);
+   k_mtf_encode<<<gw, 256, 0, st>>>(p);                 BZ_KCHECK(e);
+   k_rle2_count<<<gt, 128, 0, st>>>(p);                 BZ_KCHECK(e);
+   k_rle2_scan<<<(nb + 63) / 64, 64, 0, st>>>(p, nb);   BZ_KCHECK(e);
+   k_rle2_emit<<<gt, 128, 0, st>>>(p);                  BZ_KCHECK(e);
+   return 0;
+}
+
+} // namespace bz

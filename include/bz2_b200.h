@@ -1,0 +1,96 @@
+/*
+ * bz2_b200.h -- C ABI of the B200 (sm_100a) bzip2 compression engine.
+ *
+ * This is the boundary the libbz2-compatible front end (include/bzlib.h,
+ * bzip2_b200/csrc/bzlib_api.c) sits on, and what a maintainer of the reference
+ * would bind instead of its CPU block codec.  Plain pointers and sizes only.
+ *
+ * What each entry point replaces in the reference (aeb1787/bzip2):
+ *   bz2b200_engine_create / _destroy   the allocation half of BZ2_bzCompressInit /
+ *                                      BZ2_bzCompressEnd            (bzlib.c:144-207, :458-474)
+ *   bz2b200_compress_host              handle_compress driven to completion: RLE1 + CRC
+ *                                      (copy_input_until_stop, bzlib.c:211-315) and
+ *                                      BZ2_compressBlock per block (compress.c:822-881),
+ *                                      i.e. the body of BZ2_bzBuffToBuffCompress (bzlib.c:1309-1357)
+ *   bz2b200_compress_device            same, input and output resident in HBM
+ *   bz2b200_stream_*                   the same work fed in pieces (BZ2_bzCompress with
+ *                                      BZ_RUN / BZ_FLUSH / BZ_FINISH, bzlib.c:400-454)
+ *   bz2b200_debug_*                    per-stage intermediates for parity tests (the
+ *                                      reference exposes these only as EState fields,
+ *                                      bzlib_private.h:226-288)
+ *
+ * All functions return 0 on success or a negative BZ2B200_E* code; the text of
+ * the last error is available from bz2b200_last_error().  There is no CPU
+ * fallback: without a usable CUDA device every call fails with BZ2B200_ENODEV.
+ */
+#ifndef BZ2_B200_H
+#define BZ2_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BZ2B200_OK        0
+#define BZ2B200_EPARAM   (-1)
+#define BZ2B200_ENODEV   (-2)   /* no CUDA device / driver: the product has no CPU path  */
+#define BZ2B200_ENOMEM   (-3)
+#define BZ2B200_ECUDA    (-4)
+#define BZ2B200_EOUTFULL (-5)   /* destination too small                                  */
+#define BZ2B200_EINTERNAL (-6)
+
+typedef struct bz2b200_engine bz2b200_engine;
+
+/* Flags for the one-shot calls. */
+#define BZ2B200_TAIL_STREAMED 1u  /* last input byte was handed over in BZ_RUN mode (CLI-style
+                                     streaming); default is BuffToBuff semantics, where a lone
+                                     final byte joins a block that has just filled
+                                     (bzlib.c:276-308)                                         */
+
+typedef struct {
+   uint64_t in_bytes, out_bytes;
+   uint32_t n_blocks, n_windows;
+   uint64_t sum_nblock;          /* post-RLE1 bytes  (rho = sum_nblock / in_bytes)           */
+   uint64_t sum_nmtf;            /* MTF symbols      (mu  = sum_nmtf / sum_nblock)           */
+   uint32_t n_power_blocks;      /* blocks that were an exact power u^q                      */
+   uint32_t combined_crc;
+   float    ms_total, ms_s1, ms_s2, ms_s3, ms_s4;   /* CUDA-event times, summed over windows */
+   uint32_t bwt_rounds;          /* prefix-doubling rounds, summed over windows              */
+   uint32_t kernel_launches;
+} bz2b200_stats;
+
+int  bz2b200_device_count(void);
+const char* bz2b200_last_error(void);
+const char* bz2b200_version(void);
+
+/* window_bytes = 0 picks the default (128 MiB of input per window). */
+int  bz2b200_engine_create(bz2b200_engine** out, int device, int block_size_100k, size_t window_bytes);
+void bz2b200_engine_destroy(bz2b200_engine* e);
+
+/* Whole-stream compression, host buffers.  *dst_len: capacity in, bytes written out. */
+int  bz2b200_compress_host(bz2b200_engine* e, const void* src, size_t src_len,
+                           void* dst, size_t* dst_len, unsigned flags, bz2b200_stats* stats);
+
+/* Whole-stream compression, device buffers (d_dst must be 4-byte aligned and is cleared). */
+int  bz2b200_compress_device(bz2b200_engine* e, const void* d_src, size_t src_len,
+                             void* d_dst, size_t dst_cap, size_t* dst_len, unsigned flags,
+                             bz2b200_stats* stats);
+
+/* Streaming: feed input in pieces; compressed bytes are handed to `sink`.
+ * end_mode: 0 = more input will follow (BZ_RUN), 1 = flush (BZ_FLUSH: close the open
+ * block, no trailer), 2 = finish (BZ_FINISH: trailer + padding). */
+typedef int (*bz2b200_sink)(void* user, const void* bytes, size_t n);
+int  bz2b200_stream_begin(bz2b200_engine* e);
+int  bz2b200_stream_feed(bz2b200_engine* e, const void* src, size_t n, int end_mode,
+                         bz2b200_sink sink, void* user);
+
+/* Per-stage intermediates of the LAST window processed (tests only).
+ * name: "X" "P" "crc" "origptr" "power_q" "inuse" "ninuse" "nmtf" "mtffreq" "bits" "bitoff"
+ *       "enc" "bwt" "z" "mtfv" "sa" "sel" "hlen" "ngroups" */
+int  bz2b200_debug_keep(bz2b200_engine* e, int on);
+int  bz2b200_debug_fetch(bz2b200_engine* e, const char* name, void* dst, size_t cap, size_t* got);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,77 @@
+/*
+ * bzlib.h -- libbz2-compatible public interface of the B200 bzip2 compressor.
+ *
+ * Drop-in for the compression side of the reference's bzlib.h (aeb1787/bzip2
+ * bzlib.h:29-66 constants and bz_stream, :100-128 streaming calls, :204-221
+ * one-shot call, :134-199 stdio write calls).  Names, argument meaning, return
+ * codes and the bz_stream layout are the reference's, so existing callers
+ * relink unchanged; the work behind them runs on the GPU (see bz2_b200.h).
+ * Decompression entry points are provided by a small host decoder (used for
+ * round-trip checks); they are outside the accelerated path.
+ */
+#ifndef BZ2_B200_BZLIB_H
+#define BZ2_B200_BZLIB_H
+
+#include <stdio.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* actions for BZ2_bzCompress */
+enum { BZ_RUN = 0, BZ_FLUSH = 1, BZ_FINISH = 2 };
+
+/* return codes */
+enum {
+   BZ_OK = 0, BZ_RUN_OK = 1, BZ_FLUSH_OK = 2, BZ_FINISH_OK = 3, BZ_STREAM_END = 4,
+   BZ_SEQUENCE_ERROR = -1, BZ_PARAM_ERROR = -2, BZ_MEM_ERROR = -3, BZ_DATA_ERROR = -4,
+   BZ_DATA_ERROR_MAGIC = -5, BZ_IO_ERROR = -6, BZ_UNEXPECTED_EOF = -7,
+   BZ_OUTBUFF_FULL = -8, BZ_CONFIG_ERROR = -9
+};
+
+#define BZ_MAX_UNUSED 5000
+
+/* Caller-owned stream cursor; field order and types are ABI (reference bzlib.h:48-66). */
+typedef struct {
+   char*        next_in;
+   unsigned int avail_in;
+   unsigned int total_in_lo32;
+   unsigned int total_in_hi32;
+
+   char*        next_out;
+   unsigned int avail_out;
+   unsigned int total_out_lo32;
+   unsigned int total_out_hi32;
+
+   void*        state;
+
+   void* (*bzalloc)(void*, int, int);
+   void  (*bzfree)(void*, void*);
+   void*        opaque;
+} bz_stream;
+
+typedef void BZFILE;
+
+/* streaming compression (reference bzlib.c:144-207, :400-454, :458-474) */
+int BZ2_bzCompressInit(bz_stream* strm, int blockSize100k, int verbosity, int workFactor);
+int BZ2_bzCompress(bz_stream* strm, int action);
+int BZ2_bzCompressEnd(bz_stream* strm);
+
+/* one-shot compression (reference bzlib.c:1309-1357) */
+int BZ2_bzBuffToBuffCompress(char* dest, unsigned int* destLen, char* source, unsigned int sourceLen,
+                             int blockSize100k, int verbosity, int workFactor);
+
+/* stdio write side (reference bzlib.c:978-1146) */
+BZFILE* BZ2_bzWriteOpen(int* bzerror, FILE* f, int blockSize100k, int verbosity, int workFactor);
+void    BZ2_bzWrite(int* bzerror, BZFILE* b, void* buf, int len);
+void    BZ2_bzWriteClose(int* bzerror, BZFILE* b, int abandon, unsigned int* nbytes_in, unsigned int* nbytes_out);
+void    BZ2_bzWriteClose64(int* bzerror, BZFILE* b, int abandon,
+                           unsigned int* nbytes_in_lo32, unsigned int* nbytes_in_hi32,
+                           unsigned int* nbytes_out_lo32, unsigned int* nbytes_out_hi32);
+
+const char* BZ2_bzlibVersion(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

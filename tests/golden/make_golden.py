@@ -1,0 +1,81 @@
+"""Regenerates tests/golden/*.json from the UNMODIFIED reference (oracle/_ref/libbz2_ref.so).
+
+Run in the authoring container only (needs /root/reference to have been compiled by
+`make -C oracle ref`).  The GPU box has no reference tree; it uses the committed files.
+
+  sample{1,2,3}.ref / .bz2   the reference's own known-answer vectors (Makefile:58-66), copied verbatim
+  streams.json               sha256 + length of the reference's output for seeded synthetic inputs
+  origptr_powers.json        the reference's origPtr on exact-power blocks u^q
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import support as S  # noqa: E402
+
+
+def stream_cases():
+    """(name, bytes-like, level) -- every generator is seeded and lives in support.py / oracle/datagen.c"""
+    rng = np.random.default_rng(12345)
+    yield "empty", np.zeros(0, np.uint8), 9
+    yield "one_byte", np.array([97], np.uint8), 9
+    yield "text_200k_L1", S.gen_text(200_000), 1
+    yield "text_200k_L9", S.gen_text(200_000), 9
+    yield "text_2M_L9", S.gen_text(2_000_000), 9
+    yield "text_1M_L3", S.gen_text(1_000_000, seed=99), 3
+    yield "random_300k_L2", S.gen_random(300_000), 2
+    yield "random_1M_L9", S.gen_random(1_000_000, seed=5), 9
+    yield "period1000_1M_L9", S.gen_period1000(1_000_000), 9
+    yield "period1000_500k_L1", S.gen_period1000(500_000), 1
+    yield "aab_1M_L9", S.gen_tile(1_000_000, b"aab"), 9
+    yield "runs_4M_L9", S.gen_runs(4_000_000), 9
+    yield "runs_1M_L1", S.gen_runs(1_000_000, seed=11), 1
+    yield "mixed_3M_L5", S.gen_mixed(3_000_000, seg=1 << 18), 5
+    yield "fb_2M_L9", np.full(2_000_000, 251, np.uint8), 9
+    for k in (254, 255, 256, 257, 600):
+        yield f"run{k}_L9", np.concatenate([np.full(k, 65, np.uint8), np.array([66, 67], np.uint8)]), 9
+    yield "alpha2_50k_L9", rng.integers(0, 2, 50_000, dtype=np.uint8), 9
+    yield "alpha256_70k_L1", rng.integers(0, 256, 70_000, dtype=np.uint8), 1
+    # block-fill corner: block fills exactly one byte before the end (bzlib.c:276-308)
+    yield "tailmerge_L1", (np.arange(99981 + 1, dtype=np.uint32) % 251).astype(np.uint8), 1
+    yield "tailmerge2_L1", (np.arange(99981 + 2, dtype=np.uint32) % 251).astype(np.uint8), 1
+
+
+def power_cases():
+    units = [b"ab", b"ba", b"abc", b"aab", b"cab", b"abcabd", b"1234567", b"a", b"zyx", b"abab"]
+    qs = [2, 3, 8, 9, 10, 11, 12, 100, 1000, 1024, 1025, 2048, 2049, 5000]
+    for u in units:
+        for q in qs:
+            if len(u) * q <= 60000:
+                yield u, q
+    yield b"abc", 33327
+    yield b"ab", 449990
+    yield b"abc", 299993
+    yield b"abcabd", 149996
+    yield b"cab", 299993
+
+
+def main():
+    streams = {}
+    for name, data, level in stream_cases():
+        out = S.ref_compress(data, level)
+        streams[name] = {"level": level, "n": int(S.as_u8(data).size), "out_len": len(out),
+                         "sha256": hashlib.sha256(out).hexdigest()}
+        print(name, len(out))
+    json.dump(streams, open(os.path.join(HERE, "streams.json"), "w"), indent=1, sort_keys=True)
+    powers = []
+    for u, q in power_cases():
+        blk = np.frombuffer(u * q, np.uint8)
+        _, op = S.ref_bwt(blk)
+        powers.append({"unit": u.decode(), "q": q, "orig_ptr": int(op)})
+    json.dump(powers, open(os.path.join(HERE, "origptr_powers.json"), "w"), indent=0)
+    print(len(powers), "power cases")
+
+
+if __name__ == "__main__":
+    main()
