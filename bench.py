@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py -- compress MB/s at -9 (BASELINE.json metric), one JSON line on rank 0.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload text|random|period1000|aab|runs|mixed]
+                  [--mb 1000] [--level 9]
+
+A "step" is one pass of the whole compression path (RLE1+CRC -> BWT -> MTF/RLE2 -> Huffman -> stream)
+over one synthetic input of --mb MB (default: the 1 GB Zipf text of SURVEY.md 8(d) C2, BASELINE.json configs[1]).
+
+  value  MB/s of input, input and output resident in HBM (bz2b200_compress_device), CUDA events on the
+         stream the kernels run on, max over ranks
+  e2e    the same metric through BZ2_bzBuffToBuffCompress with pinned HOST buffers (H2D + D2H inside)
+  roofline      dominant stage (BWT) and whole pass against the measured HBM copy bandwidth
+  cpu_baseline  the reference's own CPU path (oracle/_ref) on a bounded sample, single thread
+
+With --impl reference the reference CPU implementation (oracle/_ref, else the oracle port) is timed on all
+host threads on a bounded sample of the same workload.  N>1: one process per GPU (torchrun), each rank
+compresses its own shard of the same size (weak scaling, no collective on the data path).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+
+def make_input(workload, n, rank=0):
+    import support as S
+    seed = S.TEXT_SEED + rank
+    if workload == "text":
+        return S.gen_text(n, seed=seed)
+    if workload == "random":
+        return S.gen_random(n, seed=2 + rank)
+    if workload == "period1000":
+        return S.gen_period1000(n)
+    if workload == "aab":
+        return S.gen_tile(n, b"aab")
+    if workload == "runs":
+        return S.gen_runs(n, seed=3 + rank)
+    if workload == "mixed":
+        return S.gen_mixed(n, seg=64 << 20)
+    raise SystemExit(f"unknown workload {workload}")
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.rows = []
+        self.stop = False
+        self.index = index
+        self.th = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.th.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        mx = max(int(r[1]) for r in self.rows if r[1].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[2 + k].lower().startswith("active") for r in self.rows if len(r) > 2 + k)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_reference_rate(data, level, threads, seconds_budget, sample_bytes):
+    """Reference CPU path on `threads` host threads, each compressing its own contiguous slice of a bounded
+    sample (pbzip2-style independent streams).  Returns (MB/s, kind, sample description)."""
+    import support as S
+    from concurrent.futures import ThreadPoolExecutor
+    use_ref = S.have_ref()
+    lib = S.ref() if use_ref else S.oracle()
+    sample = data[: min(sample_bytes, data.size)]
+    per = sample.size // threads
+    outs = [np.empty(int(per * 1.02) + 70000, np.uint8) for _ in range(threads)]
+
+    def work(t):
+        sl = sample[t * per:(t + 1) * per]
+        if use_ref:
+            n = C.c_uint(outs[t].size)
+            rc = lib.BZ2_bzBuffToBuffCompress(S._p(outs[t]), C.byref(n), S._p(sl), sl.size, level, 0, 0)
+            assert rc == 0
+            return n.value
+        return lib.orc_compress(S._p(sl), sl.size, level, 1, None, S._p(outs[t]), outs[t].size)
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(work, range(threads)))
+    dt = time.perf_counter() - t0
+    kind = "reference" if use_ref else "port"
+    return per * threads / dt / 1e6, kind, f"{per * threads} B prefix of the workload as {threads} independent slice(s), -{level}, one pass, {dt:.1f} s"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="text")
+    ap.add_argument("--mb", type=int, default=1000)
+    ap.add_argument("--level", type=int, default=9)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n = args.mb * 1_000_000
+    metric = "compress MB/s at -9 (1/2/4/8 B200) vs host libbz2; byte-exact .bz2 output"
+    config = {"workload": f"{args.mb} MB synthetic {args.workload} (SURVEY 8d; xorshift64* seeded), blockSize100k={args.level}, "
+                          f"one shard per GPU", "l2": "input (>= 1 GB) exceeds the 126 MB L2; no flush needed",
+              "level": args.level, "bytes_per_gpu": n}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        threads = os.cpu_count() or 1
+        sample_bytes = min(n, threads * 24_000_000)
+        data = make_input(args.workload, sample_bytes)
+        vals = []
+        info = None
+        for it in range(args.warmup + args.steps):
+            v, kind, sample = cpu_reference_rate(data, args.level, threads, 30, sample_bytes)
+            if it >= args.warmup:
+                vals.append(v)
+            info = (kind, sample)
+            if it == 0 and v * 0 == 0 and sample_bytes / (v * 1e6) > 40:   # keep the whole run within minutes
+                args.warmup, args.steps = min(args.warmup, 1), min(args.steps, 2)
+        v = sum(vals) / len(vals)
+        line = {"impl": "reference", "metric": metric, "value": round(v, 2), "unit": "MB/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sample_bytes / (v * 1e6) * 1e3, 2),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": config,
+                "cpu_baseline": {"value": round(v, 2), "unit": "MB/s", "cores": threads, "kind": info[0], "sample": info[1]},
+                "e2e": {"value": round(v, 2), "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm (GPU)
+    import torch
+    import bzip2_b200 as B
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    data = make_input(args.workload, n, rank)
+    h_in = torch.from_numpy(data).pin_memory()
+    d_in = h_in.cuda(non_blocking=False)
+    cap = n + n // 50 + 24576 * (n // (100000 * args.level - 19) + 2) + 1024
+    cap = (cap + 255) & ~255
+    d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    h_out = torch.empty(cap, dtype=torch.uint8).pin_memory()
+
+    eng = B.Engine(level=args.level, device=local_rank)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    out_len = 0
+    for _ in range(args.warmup):
+        out_len = eng.compress_device(d_in.data_ptr(), n, d_out.data_ptr(), cap)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage_ms = np.zeros(5)
+    launches = 0
+    with ClockSampler(local_rank) as clk:
+        ev0.record(stream)
+        for _ in range(args.steps):
+            out_len = eng.compress_device(d_in.data_ptr(), n, d_out.data_ptr(), cap)
+            st = eng.stats
+            stage_ms += np.array([st.ms_total, st.ms_s1, st.ms_s2, st.ms_s3, st.ms_s4])
+            launches += st.kernel_launches
+        ev1.record(stream)
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    ms_per_step = ms_max / args.steps
+    value = world * n / (ms_per_step * 1e-3) / 1e6
+    st = eng.stats
+    stage_ms /= args.steps
+
+    # end to end through the libbz2 entry point with host buffers
+    e2e = None
+    if not args.no_e2e:
+        eng.set_stream(None)
+        lib = B.load()
+        # BZ2_bzBuffToBuffCompress takes 32-bit lengths; the engine pool keeps the HBM allocation between calls
+        dlen = C.c_uint(min(cap, 0xFFFFFFFF))
+        for _ in range(max(1, min(args.warmup, 2))):
+            dlen = C.c_uint(min(cap, 0xFFFFFFFF))
+            rc = lib.BZ2_bzBuffToBuffCompress(h_out.data_ptr(), C.byref(dlen), h_in.data_ptr(), n, args.level, 0, 0)
+            assert rc == 0, rc
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            dlen = C.c_uint(min(cap, 0xFFFFFFFF))
+            rc = lib.BZ2_bzBuffToBuffCompress(h_out.data_ptr(), C.byref(dlen), h_in.data_ptr(), n, args.level, 0, 0)
+            assert rc == 0, rc
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": round(world * n * args.steps / dt / 1e6, 2), "unit": "MB/s", "h2d_bytes_per_step": n,
+               "d2h_bytes_per_step": int(dlen.value), "api": "BZ2_bzBuffToBuffCompress, pinned host buffers"}
+        # the host path must give the same bytes as the device path
+        same = bytes(h_out[: dlen.value].numpy()[:4096]) == bytes(d_out[:4096].cpu().numpy())
+        assert dlen.value == out_len and same, "host and device paths disagree"
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+    rho = st.sum_nblock / max(1, st.in_bytes)
+    mu = st.sum_nmtf / max(1, st.sum_nblock)
+    c = st.out_bytes / max(1, st.in_bytes)
+    A = 1 + 4 * rho + 12 * rho * mu + 3 * c              # algorithmic bytes per input byte, whole pass
+    s2_bytes = 2 * rho * n                               # BWT stage: read block once, write last column once
+    roof = {"bound": "hbm", "kernel": "S2 BWT stage (bigram bucket + prefix-doubling kernels)",
+            "achieved": round(s2_bytes / (stage_ms[2] * 1e-3) / 1e9, 3), "peak": peak, "unit": "GB/s",
+            "frac": round(s2_bytes / (stage_ms[2] * 1e-3) / 1e9 / peak, 6), "traffic": None, "peak_source": peak_src,
+            "whole_pass": {"A_bytes_per_input_byte": round(A, 3), "rho": round(rho, 4), "mu": round(mu, 4), "c": round(c, 4),
+                           "achieved": round(A * n / (stage_ms[0] * 1e-3) / 1e9, 3),
+                           "frac": round(A * n / (stage_ms[0] * 1e-3) / 1e9 / peak, 6)},
+            "stage_ms": {"s1_rle_crc": round(float(stage_ms[1]), 3), "s2_bwt": round(float(stage_ms[2]), 3),
+                         "s3_mtf": round(float(stage_ms[3]), 3), "s4_huffman_pack": round(float(stage_ms[4]), 3),
+                         "sum_events": round(float(stage_ms[0]), 3)}}
+    cpu = None
+    if not args.no_cpu:
+        v, kind, sample = cpu_reference_rate(data, args.level, 1, 20, 200_000_000)
+        cpu = {"value": round(v, 2), "unit": "MB/s", "cores": 1, "kind": kind, "sample": sample}
+    line = {"metric": metric, "value": round(value, 2), "unit": "MB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config, "clocks": clk.summary(),
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+            "out_bytes": int(out_len), "blocks": int(st.n_blocks), "bwt_rounds": int(st.bwt_rounds)}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -42,7 +42,7 @@ def build_library(verbose=False):
 EXPORTS = [
     # include/bz2_b200.h
     "bz2b200_device_count", "bz2b200_last_error", "bz2b200_version", "bz2b200_engine_create",
-    "bz2b200_engine_destroy", "bz2b200_compress_host", "bz2b200_compress_device", "bz2b200_stream_begin",
+    "bz2b200_engine_destroy", "bz2b200_engine_set_stream", "bz2b200_compress_host", "bz2b200_compress_device", "bz2b200_stream_begin",
     "bz2b200_stream_feed", "bz2b200_debug_keep", "bz2b200_debug_fetch",
     # include/bzlib.h
     "BZ2_bzCompressInit", "BZ2_bzCompress", "BZ2_bzCompressEnd", "BZ2_bzBuffToBuffCompress",
@@ -63,6 +63,8 @@ def load():
     lib.bz2b200_engine_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, sz]
     lib.bz2b200_engine_destroy.restype = None
     lib.bz2b200_engine_destroy.argtypes = [vp]
+    lib.bz2b200_engine_set_stream.restype = C.c_int
+    lib.bz2b200_engine_set_stream.argtypes = [vp, vp]
     lib.bz2b200_compress_host.restype = C.c_int
     lib.bz2b200_compress_host.argtypes = [vp, vp, sz, vp, C.POINTER(sz), C.c_uint, C.POINTER(Stats)]
     lib.bz2b200_compress_device.restype = C.c_int
@@ -114,6 +116,9 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+    def set_stream(self, cuda_stream_ptr):
+        _check(self.lib.bz2b200_engine_set_stream(self.h, cuda_stream_ptr), "set_stream")
 
     def compress(self, data, flags=0):
         a = np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray)) else np.ascontiguousarray(data, np.uint8)

@@ -77,7 +77,7 @@ static void engine_free(EngineFull* e)
    if (e->h_in) cudaFreeHost(e->h_in);
    if (e->h_out) cudaFreeHost(e->h_out);
    for (int i = 0; i < 6; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
-   if (e->stream) cudaStreamDestroy(e->stream);
+   if (e->own_stream) cudaStreamDestroy(e->own_stream);
    free(e);
 }
 
@@ -111,8 +111,9 @@ static int engine_new(EngineFull** out, int device, int level, size_t window_byt
       const size_t E = e->enc_cap, B = e->blk_cap;
       const size_t tiles_max = (e->nmax + 16 + MTF_TILE - 1) / MTF_TILE;
       const size_t ntiles = window_bytes / 4096 + 4;
-      cudaError_t c0 = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+      cudaError_t c0 = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking);
       if (c0 != cudaSuccess) { rc = engine_fail(e, c0, __FILE__, __LINE__); goto fail; }
+      e->stream = e->own_stream;
       for (int i = 0; i < 6; i++) cudaEventCreate(&e->ev[i]);
       ALLOC(e->enc, E + 64); ALLOC(e->cend, E + 64);
       ALLOC(e->sa, E + 64); ALLOC(e->rank, E + 64); ALLOC(e->nrank, E + 64);
@@ -170,6 +171,8 @@ static int ensure_staging(EngineFull* e, bool need_hin)
 static void stream_reset(EngineFull* e)
 {
    memset(&e->ss, 0, sizeof e->ss);
+   e->launches = 0;
+   e->bwt_rounds = 0;
 }
 
 // One window through all stages.  d_in: device input; writes coded blocks into d_out at
@@ -210,6 +213,8 @@ static int run_window(EngineFull* e, const u8* d_in, u32 W, bool is_final, bool 
    ss.block_no += nb;
    ss.bits = end_bit;
    ss.st.n_blocks += nb; ss.st.n_windows++; ss.st.sum_nblock += E;
+   ss.st.kernel_launches = e->launches;
+   ss.st.bwt_rounds = e->bwt_rounds;
    float ms;
    cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]); ss.st.ms_s1 += ms;
    cudaEventElapsedTime(&ms, e->ev[1], e->ev[2]); ss.st.ms_s2 += ms;
@@ -438,6 +443,14 @@ int bz2b200_stream_feed(bz2b200_engine* h, const void* src, size_t n, int end_mo
    if (end_mode == 2) {
       if ((rc = finish_stream(e, sk))) return rc;
    }
+   return 0;
+}
+
+int bz2b200_engine_set_stream(bz2b200_engine* h, void* cuda_stream)
+{
+   EngineFull* e = reinterpret_cast<EngineFull*>(h);
+   if (!e) return set_err(BZ2B200_EPARAM, "null engine");
+   e->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : e->own_stream;
    return 0;
 }
 

@@ -69,7 +69,10 @@ struct Engine {
    int level;
    u32 nmax;               // 100000*level - 19   (bzlib.c:190)
    cudaStream_t stream;
+   cudaStream_t own_stream;   // created by the engine; `stream` may be replaced by the caller's
    int num_sms;
+   u32 launches;              // kernels launched since the stream was reset
+   u32 bwt_rounds;            // prefix-doubling rounds since the stream was reset
 
    // capacities
    u32 win_cap;            // max input bytes per window
@@ -123,6 +126,6 @@ struct Engine {
 int engine_fail(Engine* e, cudaError_t c, const char* file, int line);
 
 #define BZ_CUDA(e, call) do { cudaError_t c_ = (call); if (c_ != cudaSuccess) return engine_fail((e), c_, __FILE__, __LINE__); } while (0)
-#define BZ_KCHECK(e) BZ_CUDA(e, cudaGetLastError())
+#define BZ_KCHECK(e) do { (e)->launches++; BZ_CUDA(e, cudaGetLastError()); } while (0)
 
 } // namespace bz

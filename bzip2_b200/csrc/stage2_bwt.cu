@@ -573,6 +573,10 @@ int stage2_run(Engine* e, u32 nb, u32 E)
       if (cnt[2]) launch_small<8>(e, p, Lout, si[2], cnt[2], h);
       if (cnt[1]) launch_small<4>(e, p, Lout, si[1], cnt[1], h);
       if (cnt[0]) launch_small<2>(e, p, Lout, si[0], cnt[0], h);
+      u32 nl = 0;
+      for (int c = 0; c < N_CLASSES; c++) nl += cnt[c] ? 1u : 0u;
+      e->launches += nl - 1;
+      e->bwt_rounds++;
       BZ_KCHECK(e);
       if (cnt[CLS_LARGE]) k_apply_big<<<cnt[CLS_LARGE], 256, 0, st>>>(p, bi[2]);
       if (cnt[CLS_MED2])  k_apply_big<<<cnt[CLS_MED2], 256, 0, st>>>(p, bi[1]);
@@ -582,6 +586,7 @@ int stage2_run(Engine* e, u32 nb, u32 E)
       if (cnt[2]) launch_apply_small<8>(e, p, si[2], cnt[2]);
       if (cnt[1]) launch_apply_small<4>(e, p, si[1], cnt[1]);
       if (cnt[0]) launch_apply_small<2>(e, p, si[0], cnt[0]);
+      e->launches += nl - 1;
       BZ_KCHECK(e);
       cur = nxt;
    }

@@ -66,6 +66,8 @@ const char* bz2b200_version(void);
 /* window_bytes = 0 picks the default (128 MiB of input per window). */
 int  bz2b200_engine_create(bz2b200_engine** out, int device, int block_size_100k, size_t window_bytes);
 void bz2b200_engine_destroy(bz2b200_engine* e);
+/* Run on the caller's CUDA stream (a cudaStream_t); NULL restores the engine's own stream. */
+int  bz2b200_engine_set_stream(bz2b200_engine* e, void* cuda_stream);
 
 /* Whole-stream compression, host buffers.  *dst_len: capacity in, bytes written out. */
 int  bz2b200_compress_host(bz2b200_engine* e, const void* src, size_t src_len,
