@@ -61,7 +61,7 @@ static void engine_free(EngineFull* e)
    if (!e) return;
    cudaSetDevice(e->device);
    void* dev[] = { e->enc, e->cend, e->sa, e->rank, e->nrank, e->keyA, e->keyB, e->idxB, e->bwt, e->z, e->mtfv, e->hist,
-                   e->blockmap, e->tile_len, e->tile_ext, e->tile_carry, e->tile_size, e->tile_base, e->s1_scalars,
+                   e->blockmap, e->code, e->kk, e->nbins, e->tile_len, e->tile_ext, e->tile_carry, e->tile_size, e->tile_base, e->s1_scalars,
                    e->mtf_summary, e->mtf_tilemeta, e->mtf_tilecnt, e->sel, e->hlen, e->hfreq, e->hcode, e->grpbits,
                    e->pre, e->prebits, e->ngroups, e->d_in, e->d_out,
                    e->bt.X, e->bt.P, e->bt.crc, e->bt.origptr, e->bt.power_q, e->bt.inuse, e->bt.ninuse, e->bt.nmtf,
@@ -119,7 +119,10 @@ static int engine_new(EngineFull** out, int device, int level, size_t window_byt
       ALLOC(e->sa, E + 64); ALLOC(e->rank, E + 64); ALLOC(e->nrank, E + 64);
       ALLOC(e->keyA, E + 64); ALLOC(e->keyB, E + 64); ALLOC(e->idxB, E + 64);
       ALLOC(e->bwt, E + 64); ALLOC(e->z, E + 64); ALLOC(e->mtfv, E + B + 64);
-      ALLOC(e->hist, B * 65536);
+      e->hist_stride = 1u << 16;
+      while (e->hist_stride < (1u << 18) && e->hist_stride < e->nmax / 4) e->hist_stride <<= 1;
+      ALLOC(e->hist, B * e->hist_stride);
+      ALLOC(e->code, B * 256); ALLOC(e->kk, B); ALLOC(e->nbins, B);
       ALLOC(e->blockmap, E / 4096 + 4);
       ALLOC(e->tile_len, ntiles); ALLOC(e->tile_ext, ntiles); ALLOC(e->tile_carry, ntiles);
       ALLOC(e->tile_size, ntiles); ALLOC(e->tile_base, ntiles);
@@ -136,7 +139,7 @@ static int engine_new(EngineFull** out, int device, int level, size_t window_byt
       ALLOC(e->bt.bits, B); ALLOC(e->bt.bitoff, B + 2);
       static const u32 minlen[N_SMALL_CLASSES] = {2, 3, 5, 9, 17};
       for (int c = 0; c < N_SMALL_CLASSES; c++) e->lists.small_cap[c] = (u32)(E / minlen[c] + 1024);
-      e->lists.big_cap[0] = (u32)(E / 33 + 1024); e->lists.big_cap[1] = (u32)(E / 513 + 1024); e->lists.big_cap[2] = (u32)(E / 4097 + 1024);
+      e->lists.big_cap[0] = (u32)(E / 33 + 1024); e->lists.big_cap[1] = (u32)(E / 257 + 1024); e->lists.big_cap[2] = (u32)(E / 4097 + 1024);
       for (int w = 0; w < 2; w++) {
          for (int c = 0; c < N_SMALL_CLASSES; c++) ALLOC(e->lists.small_items[w][c], e->lists.small_cap[c]);
          for (int c = 0; c < 3; c++) ALLOC(e->lists.big_items[w][c], e->lists.big_cap[c]);

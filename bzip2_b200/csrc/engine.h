@@ -12,18 +12,18 @@
 //   nrank u32[E]    new ranks by sorted position (applied after each refinement round)
 //   keyA/keyB/idxB  u32[E] scratch for the large-segment radix path
 //   bwt   u8 [E]    last column;   z u8[E]  MTF positions;   mtfv u16[E + 2*nb]
-//   hist  u32[nb*65536]  bigram bucket histogram / cursors
+//   hist  u32[nb*hist_stride]  k-gram bucket histogram / cursors
 #pragma once
 #include "common.cuh"
 
 namespace bz {
 
 constexpr int N_SMALL_CLASSES = 5;          // segment lengths 2, 3-4, 5-8, 9-16, 17-32
-constexpr int CLS_MED1 = 5;                 // 33..512
-constexpr int CLS_MED2 = 6;                 // 513..4096
+constexpr int CLS_MED1 = 5;                 // 33..256  (one warp, registers)
+constexpr int CLS_MED2 = 6;                 // 257..4096 (one CTA)
 constexpr int CLS_LARGE = 7;                // > 4096
 constexpr int N_CLASSES = 8;
-constexpr u32 MED1_MAX = 512;
+constexpr u32 MED1_MAX = 256;
 constexpr u32 MED2_MAX = 4096;
 constexpr u32 MAX_BLOCKS = 4096;            // block id must fit 12 bits in a segment entry
 constexpr u32 MAX_ENC = 1u << 27;           // flat position must fit 27 bits in a small entry
@@ -85,6 +85,9 @@ struct Engine {
    u8  *bwt, *z;
    u16 *mtfv;
    u32 *hist;
+   u32 hist_stride;        // k-gram bins reserved per block (power of two, 2^16..2^18)
+   u8  *code;              // [blk_cap*256]
+   u32 *kk, *nbins;        // [blk_cap]
    u32 *blockmap;          // [enc_cap/4096 + 2] block id of each 4 KiB chunk of enc
    SegLists lists;
    BlockTables bt;

@@ -44,6 +44,10 @@ struct S2Params {
    u32* sa; u32* rank; u32* nrank;
    u32* keyA; u32* keyB; u32* idxB;
    u32* hist;
+   u32 hist_stride;         // bins reserved per block
+   u8* code;                // [nb*256] dense symbol codes
+   u32* kk;                 // [nb] k of the k-gram bucket sort = initial sorted depth
+   u32* nbins;              // [nb] ninuse^k
    const u32* blockmap;
    u32* power_q;
    u8* inuse; u32* ninuse;
@@ -96,69 +100,123 @@ __global__ void k_blockmap(const u32* X, u32 nb, u32* blockmap, u32 nchunks)
    blockmap[c] = lo;
 }
 
-// ---- 1. bigram bucket sort -----------------------------------------------------
-constexpr int BG_THREADS = 256;
-constexpr int BG_ITEMS = 16;
-constexpr int BG_TILE = BG_THREADS * BG_ITEMS;
+// ---- 1. k-gram bucket sort ------------------------------------------------------------
+// The first k symbols of every rotation are packed in base-`ninuse` positional notation
+// (k = the largest power that keeps ninuse^k within the per-block bin budget), so text
+// with 61 symbols starts at depth 3, a binary alphabet at depth 18, full-byte data at 2.
+constexpr int KG_THREADS = 256;
+constexpr int KG_ITEMS = 16;
+constexpr int KG_TILE = KG_THREADS * KG_ITEMS;
+constexpr int KG_MAXK = 24;
 
-enum { BG_HIST = 0, BG_RANK = 1, BG_SCATTER = 2 };
+enum { KG_HIST = 0, KG_RANK = 1, KG_SCATTER = 2 };
 
-template <int MODE>
-__global__ void __launch_bounds__(BG_THREADS) k_bigram(S2Params p)
+__global__ void __launch_bounds__(KG_THREADS) k_inuse(S2Params p)
 {
+   __shared__ u32 flags[256];
    const u32 b = blockIdx.y;
    const u32 xb = p.X[b], n = p.X[b + 1] - xb;
-   const u32 t0 = blockIdx.x * BG_TILE;
+   const u32 t0 = blockIdx.x * KG_TILE;
+   if (t0 >= n) return;
+   flags[threadIdx.x] = 0;
+   __syncthreads();
+   const u8* T = p.T + xb;
+#pragma unroll 4
+   for (int k = 0; k < KG_ITEMS; k++) {
+      const u32 i = t0 + k * KG_THREADS + threadIdx.x;
+      if (i < n) flags[T[i]] = 1;
+   }
+   __syncthreads();
+   if (flags[threadIdx.x]) p.inuse[(size_t)b * 256 + threadIdx.x] = 1;
+}
+
+// dense symbol codes, alphabet size, k and bin count of every block
+__global__ void __launch_bounds__(256) k_codemap(S2Params p)
+{
+   __shared__ u32 wcnt[8];
+   const u32 b = blockIdx.x, tid = threadIdx.x, w = tid >> 5, l = lane_id();
+   const bool used = p.inuse[(size_t)b * 256 + tid] != 0;
+   const u32 bal = __ballot_sync(FULL, used);
+   if (l == 0) wcnt[w] = __popc(bal);
+   __syncthreads();
+   u32 base = 0, tot = 0;
+   for (u32 k = 0; k < 8; k++) { if (k < w) base += wcnt[k]; tot += wcnt[k]; }
+   p.code[(size_t)b * 256 + tid] = (u8)(used ? base + __popc(bal & lanemask_lt()) : 0);
+   if (tid == 0) {
+      p.ninuse[b] = tot;
+      u32 k = 1, bins = tot ? tot : 1;
+      while (tot > 1 && k < KG_MAXK && (u64)bins * tot <= (u64)p.hist_stride) { bins *= tot; k++; }
+      p.kk[b] = k;
+      p.nbins[b] = bins;
+   }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(KG_THREADS) k_kgram(S2Params p)
+{
+   __shared__ u8 sc[KG_TILE + KG_MAXK + 8];
+   __shared__ u8 cmap[256];
+   const u32 b = blockIdx.y;
+   const u32 xb = p.X[b], n = p.X[b + 1] - xb;
+   const u32 t0 = blockIdx.x * KG_TILE;
    if (t0 >= n) return;
    const u8* T = p.T + xb;
-   u32* hist = p.hist + (size_t)b * 65536;
-#pragma unroll 4
-   for (int k = 0; k < BG_ITEMS; k++) {
-      const u32 i = t0 + k * BG_THREADS + threadIdx.x;
+   const u32 k = p.kk[b], base = p.ninuse[b];
+   u32* hist = p.hist + (size_t)b * p.hist_stride;
+   cmap[threadIdx.x] = p.code[(size_t)b * 256 + threadIdx.x];
+   __syncthreads();
+   const u32 span = min((u32)KG_TILE, n - t0) + k - 1;
+   for (u32 s = threadIdx.x; s < span; s += KG_THREADS) {
+      u32 gi = t0 + s;
+      if (gi >= n) gi = (gi - n < n) ? gi - n : gi % n;
+      sc[s] = cmap[T[gi]];
+   }
+   __syncthreads();
+#pragma unroll 2
+   for (int it = 0; it < KG_ITEMS; it++) {
+      const u32 s = it * KG_THREADS + threadIdx.x;
+      const u32 i = t0 + s;
       if (i < n) {
-         const u32 c0 = T[i];
-         const u32 c1 = T[(i + 1 == n) ? 0 : i + 1];
-         const u32 bin = (c0 << 8) | c1;
-         if (MODE == BG_HIST) atomicAdd(&hist[bin], 1u);
-         else if (MODE == BG_RANK) p.rank[xb + i] = hist[bin];
-         else { const u32 pos = atomicAdd(&hist[bin], 1u); p.sa[xb + pos] = i; }
+         u32 key = 0;
+         for (u32 j = 0; j < k; j++) key = key * base + sc[s + j];
+         if (MODE == KG_HIST) atomicAdd(&hist[key], 1u);
+         else if (MODE == KG_RANK) p.rank[xb + i] = hist[key];
+         else { const u32 pos = atomicAdd(&hist[key], 1u); p.sa[xb + pos] = i; }
       }
    }
 }
 
-// exclusive scan of the 65536 bucket counts of one block; also the in-use byte map
-__global__ void __launch_bounds__(1024) k_bigram_scan(S2Params p)
+// exclusive scan of the bucket counts of one block
+__global__ void __launch_bounds__(1024) k_kgram_scan(S2Params p)
 {
    __shared__ u32 ssm[34];
-   __shared__ u32 rows[256];
+   __shared__ u32 s_run;
    const u32 b = blockIdx.x;
-   u32* hist = p.hist + (size_t)b * 65536;
-   if (threadIdx.x < 256) rows[threadIdx.x] = 0;
-   u32 v[64];
-   u32 sum = 0;
-   uint4* h4 = reinterpret_cast<uint4*>(hist + threadIdx.x * 64);
-#pragma unroll
-   for (int k = 0; k < 16; k++) {
-      uint4 q = h4[k];
-      v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
-      sum += q.x + q.y + q.z + q.w;
-   }
-   u32 ex = block_excl_sum<1024>(sum, ssm, nullptr);   // syncs inside also publish rows[] zeroing
-   if (sum) atomicAdd(&rows[threadIdx.x >> 2], sum);
-#pragma unroll
-   for (int k = 0; k < 16; k++) {
-      uint4 q;
-      q.x = ex; ex += v[4 * k];
-      q.y = ex; ex += v[4 * k + 1];
-      q.z = ex; ex += v[4 * k + 2];
-      q.w = ex; ex += v[4 * k + 3];
-      h4[k] = q;
-   }
+   u32* hist = p.hist + (size_t)b * p.hist_stride;
+   const u32 nbins = p.nbins[b];
+   if (threadIdx.x == 0) s_run = 0;
    __syncthreads();
-   const u32 used = (threadIdx.x < 256 && rows[threadIdx.x]) ? 1u : 0u;
-   if (threadIdx.x < 256) p.inuse[(size_t)b * 256 + threadIdx.x] = (u8)used;
-   const u32 cnt = __syncthreads_count(used);
-   if (threadIdx.x == 0) p.ninuse[b] = cnt;
+   for (u32 base = 0; base < nbins; base += 1024 * 16) {
+      const u32 lo = base + threadIdx.x * 16;
+      u32 v[16], sum = 0;
+      if (lo + 16 <= nbins) {
+         const uint4* h4 = reinterpret_cast<const uint4*>(hist + lo);
+#pragma unroll
+         for (int k = 0; k < 4; k++) { uint4 q = h4[k]; v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w; }
+      } else {
+#pragma unroll
+         for (int k = 0; k < 16; k++) v[k] = (lo + k < nbins) ? hist[lo + k] : 0;
+      }
+#pragma unroll
+      for (int k = 0; k < 16; k++) sum += v[k];
+      u32 tot;
+      u32 ex = block_excl_sum<1024>(sum, ssm, &tot) + s_run;
+#pragma unroll
+      for (int k = 0; k < 16; k++) { if (lo + k < nbins) hist[lo + k] = ex; ex += v[k]; }
+      __syncthreads();
+      if (threadIdx.x == 0) s_run += tot;
+      __syncthreads();
+   }
 }
 
 // after the scatter hist[bin] is the END of bucket `bin`; emit the initial segments
@@ -166,20 +224,21 @@ __global__ void __launch_bounds__(256) k_seg_init(S2Params p, ListsDev L)
 {
    const u32 b = blockIdx.y;
    const u32 xb = p.X[b], n = p.X[b + 1] - xb;
-   const u32* hist = p.hist + (size_t)b * 65536;
+   const u32* hist = p.hist + (size_t)b * p.hist_stride;
    const u32 bin = blockIdx.x * 256 + threadIdx.x;
-   const u32 end = hist[bin];
-   const u32 start = bin ? hist[bin - 1] : 0;
+   const bool vbin = bin < p.nbins[b];
+   const u32 end = vbin ? hist[bin] : 0;
+   const u32 start = (vbin && bin) ? hist[bin - 1] : 0;
    const u32 len = end - start;
-   const bool multi = len >= 2;
-   const bool deep = (2u >= n);                       // depth 2 already covers the whole rotation
+   const bool multi = vbin && len >= 2;
+   const bool deep = (p.kk[b] >= n);                  // depth k already covers the whole rotation
    if (multi && deep) atomicMax(&p.power_q[b], len);
    push_seg(L, multi && !deep, xb + start, b, len);
 }
 
 // ---- 2a. small segments: sub-warp bitonic network ------------------------------------
 template <int LANES>
-__global__ void __launch_bounds__(256) k_refine_small(S2Params p, ListsDev Lout, const u32* items, u32 count, u32 h)
+__global__ void __launch_bounds__(256) k_refine_small(S2Params p, ListsDev Lout, const u32* items, u32 count, u32 round)
 {
    const u32 gid = blockIdx.x * blockDim.x + threadIdx.x;
    const u32 seg = gid / LANES;
@@ -188,8 +247,8 @@ __global__ void __launch_bounds__(256) k_refine_small(S2Params p, ListsDev Lout,
    const u32 entry = vseg ? items[seg] : 0;
    const u32 pos = entry & 0x7ffffffu;
    const u32 len = (entry >> 27) + 1;
-   u32 b = 0, xb = 0, n = 1;
-   if (vseg) { b = block_of(p, pos); xb = p.X[b]; n = p.X[b + 1] - xb; }
+   u32 b = 0, xb = 0, n = 1, h = 0;
+   if (vseg) { b = block_of(p, pos); xb = p.X[b]; n = p.X[b + 1] - xb; h = p.kk[b] << round; }
    const bool active = vseg && sub < len;
    u32 idx = 0, key = 0xffffffffu;
    if (active) {
@@ -245,80 +304,155 @@ __global__ void __launch_bounds__(256) k_apply_small(S2Params p, const u32* item
    p.rank[xb + p.sa[pos + sub]] = p.nrank[pos + sub];
 }
 
-// ---- 2b. medium segments: one CTA, bitonic sort in shared memory ---------------------
-template <int CAP, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_refine_medium(S2Params p, ListsDev Lout, const u64* items, u32 h)
+// ---- 2b. medium segments: bitonic sort of packed (key, local index) words ----------------
+// Every thread owns ITEMS = 8 consecutive elements of the sequence in registers.  Compare
+// distances below 8 stay inside the thread, distances below 256 go through shuffles and
+// only distances >= 256 (other warps) go through shared memory.  The packed word makes a
+// compare-exchange a min/max pair.
+constexpr int MS_ITEMS = 8;
+
+template <int THREADS>
+__device__ __forceinline__ void bitonic_blocked(u32 (&v)[MS_ITEMS], const u32 t, const u32 n2, u32* xch)
 {
-   constexpr int ITEMS = CAP / THREADS;
-   __shared__ u32 skey[CAP];
-   __shared__ u32 sidx[CAP];
+#pragma unroll
+   for (int k = 2; k <= THREADS * MS_ITEMS; k <<= 1) {
+      if ((u32)k > n2) break;
+#pragma unroll
+      for (int j = k >> 1; j > 0; j >>= 1) {
+         if (j >= MS_ITEMS * 32) {
+            // partner lives in another warp
+            const u32 tj = (u32)j / MS_ITEMS;
+            const bool keep_min = ((((t * MS_ITEMS) & (u32)k) == 0) == ((t & tj) == 0));
+            __syncthreads();
+            reinterpret_cast<uint4*>(xch)[t * 2] = make_uint4(v[0], v[1], v[2], v[3]);
+            reinterpret_cast<uint4*>(xch)[t * 2 + 1] = make_uint4(v[4], v[5], v[6], v[7]);
+            __syncthreads();
+            const uint4 a = reinterpret_cast<const uint4*>(xch)[(t ^ tj) * 2];
+            const uint4 c = reinterpret_cast<const uint4*>(xch)[(t ^ tj) * 2 + 1];
+            const u32 o[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+            for (int r = 0; r < MS_ITEMS; r++) v[r] = keep_min ? min(v[r], o[r]) : max(v[r], o[r]);
+         } else if (j >= MS_ITEMS) {
+            const u32 lj = (u32)j / MS_ITEMS;
+            const bool keep_min = ((((t * MS_ITEMS) & (u32)k) == 0) == ((t & lj) == 0));
+#pragma unroll
+            for (int r = 0; r < MS_ITEMS; r++) {
+               const u32 o = __shfl_xor_sync(FULL, v[r], lj);
+               v[r] = keep_min ? min(v[r], o) : max(v[r], o);
+            }
+         } else {
+#pragma unroll
+            for (int r = 0; r < MS_ITEMS; r++) {
+               if ((r & j) == 0) {
+                  const bool asc = (((t * MS_ITEMS + r) & (u32)k) == 0);
+                  const u32 lo = min(v[r], v[r | j]), hi = max(v[r], v[r | j]);
+                  v[r] = asc ? lo : hi;
+                  v[r | j] = asc ? hi : lo;
+               }
+            }
+         }
+      }
+   }
+}
+
+// One segment per group of THREADS threads (THREADS = 32: a warp, no shared memory;
+// THREADS = 512: a CTA).  LBITS = bits of the local index packed under the key.
+template <int THREADS, int LBITS>
+__global__ void __launch_bounds__(THREADS == 32 ? 256 : THREADS)
+k_refine_medium(S2Params p, ListsDev Lout, const u64* items, u32 count, u32 round)
+{
+   constexpr int CAP = THREADS * MS_ITEMS;
+   constexpr bool WARP = (THREADS == 32);
+   __shared__ u32 xch[WARP ? 1 : CAP];
+   __shared__ u32 sidx[WARP ? 1 : CAP];
    __shared__ u32 ssm[34];
-   const u64 entry = items[blockIdx.x];
+   const u32 t = WARP ? lane_id() : threadIdx.x;
+   const u32 seg = WARP ? (blockIdx.x * 8 + (threadIdx.x >> 5)) : blockIdx.x;
+   const bool vseg = seg < count;
+   const u64 entry = vseg ? items[seg] : 0;
    const u32 pos = (u32)(entry >> 32);
    const u32 b = (u32)(entry >> 20) & 0xfffu;
    const u32 len = (u32)entry & 0xfffffu;
-   const u32 xb = p.X[b], n = p.X[b + 1] - xb;
+   u32 xb = 0, n = 1, h = 0;
+   if (vseg) { xb = p.X[b]; n = p.X[b + 1] - xb; h = p.kk[b] << round; }
    u32 n2 = 64;
    while (n2 < len) n2 <<= 1;
-   for (u32 i = threadIdx.x; i < n2; i += THREADS) {
-      u32 key = 0xffffffffu, idx = 0;
-      if (i < len) {
-         idx = p.sa[pos + i];
-         u32 t = idx + h; if (t >= n) t -= n;
-         key = p.rank[xb + t];
-      }
-      skey[i] = key; sidx[i] = idx;
-   }
-   __syncthreads();
-   for (u32 k = 2; k <= n2; k <<= 1) {
-      for (u32 j = k >> 1; j > 0; j >>= 1) {
-         for (u32 t = threadIdx.x; t < (n2 >> 1); t += THREADS) {
-            const u32 lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-            const u32 hi = lo | j;
-            const bool asc = ((lo & k) == 0);
-            const u32 a = skey[lo], c = skey[hi];
-            if ((a > c) == asc && a != c) {
-               skey[lo] = c; skey[hi] = a;
-               const u32 ia = sidx[lo]; sidx[lo] = sidx[hi]; sidx[hi] = ia;
-            }
-         }
-         __syncthreads();
-      }
-   }
-   // group starts: inclusive max-scan of (head ? i+1 : 0)
-   const u32 base = threadIdx.x * ITEMS;
-   u32 last = 0;
-   u32 gs[ITEMS];
+   // blocked load: thread t owns sequence positions t*8 .. t*8+7; the element's local id travels
+   // in the low bits of the packed word.  Padding (0xffffffff) sorts to the end of [0, n2).
+   u32 v[MS_ITEMS];
 #pragma unroll
-   for (int k = 0; k < ITEMS; k++) {
-      const u32 i = base + k;
+   for (int r = 0; r < MS_ITEMS; r++) {
+      const u32 i = t * MS_ITEMS + (u32)r;
+      u32 w = 0xffffffffu;
       if (i < len) {
-         const bool head = (i == 0) || (skey[i] != skey[i - 1]);
-         if (head) last = i + 1;
+         const u32 idx = p.sa[pos + i];
+         if (!WARP) sidx[i] = idx;
+         u32 tt = idx + h; if (tt >= n) tt -= n;
+         w = (p.rank[xb + tt] << LBITS) | i;
       }
-      gs[k] = last;
+      v[r] = w;
    }
-   const u32 incl = block_incl_max<THREADS>(last, ssm);
-   // exclusive value for this thread = max over previous threads; recover from warp shuffle of inclusive
-   u32 prev = __shfl_up_sync(FULL, incl, 1);
-   if (lane_id() == 0) {
-      // previous warp's inclusive max lives in ssm[w] (exclusive prefix of warps)
-      prev = ssm[threadIdx.x >> 5];
+   bitonic_blocked<THREADS>(v, t, n2, xch);
+   // sorted position e = t*8 + r.  Heads, group starts (1-based running max), ends.
+   u32 prevlast = __shfl_up_sync(FULL, v[MS_ITEMS - 1], 1);
+   if (!WARP) {
+      __syncthreads();
+      if (lane_id() == 31) xch[threadIdx.x >> 5] = v[MS_ITEMS - 1];
+      __syncthreads();
+      if (lane_id() == 0 && t > 0) prevlast = xch[(threadIdx.x >> 5) - 1];
    }
+   u32 nextfirst = __shfl_down_sync(FULL, v[0], 1);
+   if (!WARP) {
+      __syncthreads();
+      if (lane_id() == 0) xch[threadIdx.x >> 5] = v[0];
+      __syncthreads();
+      if (lane_id() == 31 && (threadIdx.x >> 5) + 1 < THREADS / 32) nextfirst = xch[(threadIdx.x >> 5) + 1];
+   }
+   const u32 base = t * MS_ITEMS;
+   u32 last = 0, gs[MS_ITEMS];
+#pragma unroll
+   for (int r = 0; r < MS_ITEMS; r++) {
+      const u32 e = base + r;
+      if (e < len) {
+         const u32 pv = (r == 0) ? prevlast : v[r - 1];
+         if (e == 0 || (pv >> LBITS) != (v[r] >> LBITS)) last = e + 1;
+      }
+      gs[r] = last;
+   }
+   u32 incl, prev;
+   if (WARP) {
+      incl = warp_incl_max(last);
+      prev = __shfl_up_sync(FULL, incl, 1);
+      if (t == 0) prev = 0;
+   } else {
+      incl = block_incl_max<THREADS>(last, ssm);
+      prev = __shfl_up_sync(FULL, incl, 1);
+      if (lane_id() == 0) prev = ssm[threadIdx.x >> 5];
+   }
+   // fetch the rotation indices before anything is overwritten
+   u32 idxs[MS_ITEMS];
+#pragma unroll
+   for (int r = 0; r < MS_ITEMS; r++) {
+      const u32 e = base + r;
+      const u32 local = v[r] & ((1u << LBITS) - 1u);
+      idxs[r] = (e < len) ? (WARP ? p.sa[pos + local] : sidx[local]) : 0;
+   }
+   if (WARP) __syncwarp(); else __syncthreads();
    const bool deep = (2u * h >= n);
 #pragma unroll
-   for (int k = 0; k < ITEMS; k++) {
-      const u32 i = base + k;
-      const bool in = i < len;
-      u32 g = gs[k] ? gs[k] : prev;          // 1-based head index
+   for (int r = 0; r < MS_ITEMS; r++) {
+      const u32 e = base + r;
+      const bool in = e < len;
+      u32 g = gs[r] ? gs[r] : prev;
       g = g ? g - 1 : 0;
       bool is_end = false;
       if (in) {
-         p.sa[pos + i] = sidx[i];
-         p.nrank[pos + i] = (pos - xb) + g;
-         is_end = (i == len - 1) || (skey[i + 1] != skey[i]);
+         p.sa[pos + e] = idxs[r];
+         p.nrank[pos + e] = (pos - xb) + g;
+         const u32 nx = (r == MS_ITEMS - 1) ? nextfirst : v[r + 1];
+         is_end = (e == len - 1) || ((nx >> LBITS) != (v[r] >> LBITS));
       }
-      const u32 size = i - g + 1;
+      const u32 size = e - g + 1;
       const bool multi = in && is_end && size >= 2;
       if (multi && deep) atomicMax(&p.power_q[b], size);
       push_seg(Lout, multi && !deep, pos + g, b, size);
@@ -331,7 +465,7 @@ constexpr int LG_ITEMS = 4;
 constexpr int LG_TILE = LG_THREADS * LG_ITEMS;
 constexpr int LG_WARPS = LG_THREADS / 32;
 
-__global__ void __launch_bounds__(LG_THREADS) k_refine_large(S2Params p, ListsDev Lout, const u64* items, u32 h)
+__global__ void __launch_bounds__(LG_THREADS) k_refine_large(S2Params p, ListsDev Lout, const u64* items, u32 round)
 {
    __shared__ u32 whist[LG_WARPS][256];
    __shared__ u32 binbase[3][256];
@@ -343,6 +477,7 @@ __global__ void __launch_bounds__(LG_THREADS) k_refine_large(S2Params p, ListsDe
    const u32 len = (u32)entry & 0xfffffu;
    const u32 xb = p.X[b], n = p.X[b + 1] - xb;
    const int npass = (n > 65536u) ? 3 : 2;
+   const u32 h = p.kk[b] << round;
    const u32 w = threadIdx.x >> 5, l = lane_id();
 
    for (u32 i = threadIdx.x; i < 3 * 256; i += LG_THREADS) (&binbase[0][0])[i] = 0;
@@ -470,6 +605,19 @@ __global__ void __launch_bounds__(LG_THREADS) k_refine_large(S2Params p, ListsDe
    }
 }
 
+// one warp per segment (33..256 elements)
+__global__ void __launch_bounds__(256) k_apply_warp(S2Params p, const u64* items, u32 count)
+{
+   const u32 seg = blockIdx.x * 8 + (threadIdx.x >> 5);
+   if (seg >= count) return;
+   const u64 entry = items[seg];
+   const u32 pos = (u32)(entry >> 32);
+   const u32 b = (u32)(entry >> 20) & 0xfffu;
+   const u32 len = (u32)entry & 0xfffffu;
+   const u32 xb = p.X[b];
+   for (u32 i = lane_id(); i < len; i += 32) p.rank[xb + p.sa[pos + i]] = p.nrank[pos + i];
+}
+
 __global__ void __launch_bounds__(256) k_apply_big(S2Params p, const u64* items)
 {
    const u64 entry = items[blockIdx.x];
@@ -481,18 +629,18 @@ __global__ void __launch_bounds__(256) k_apply_big(S2Params p, const u64* items)
 }
 
 // ---- 3. last column -------------------------------------------------------------------
-__global__ void __launch_bounds__(BG_THREADS) k_bwt_out(S2Params p, u8* bwt, u32* origptr)
+__global__ void __launch_bounds__(KG_THREADS) k_bwt_out(S2Params p, u8* bwt, u32* origptr)
 {
    const u32 b = blockIdx.y;
    const u32 xb = p.X[b], n = p.X[b + 1] - xb;
-   const u32 t0 = blockIdx.x * BG_TILE;
+   const u32 t0 = blockIdx.x * KG_TILE;
    if (t0 >= n) return;
    const u8* T = p.T + xb;
    // rank of rotation 0: its final position, or the start of its tie group for exact powers
    if (blockIdx.x == 0 && threadIdx.x == 0) origptr[b] = p.rank[xb];
 #pragma unroll 4
-   for (int k = 0; k < BG_ITEMS; k++) {
-      const u32 i = t0 + k * BG_THREADS + threadIdx.x;
+   for (int k = 0; k < KG_ITEMS; k++) {
+      const u32 i = t0 + k * KG_THREADS + threadIdx.x;
       if (i < n) {
          const u32 s = p.sa[xb + i];
          bwt[xb + i] = T[s ? s - 1 : n - 1];
@@ -512,11 +660,11 @@ static ListsDev lists_dev(Engine* e, int which)
 }
 
 template <int LANES>
-static void launch_small(Engine* e, const S2Params& p, const ListsDev& Lout, const u32* items, u32 count, u32 h)
+static void launch_small(Engine* e, const S2Params& p, const ListsDev& Lout, const u32* items, u32 count, u32 round)
 {
    const u64 threads = (u64)count * LANES;
    const u32 grid = (u32)((threads + 255) / 256);
-   k_refine_small<LANES><<<grid, 256, 0, e->stream>>>(p, Lout, items, count, h);
+   k_refine_small<LANES><<<grid, 256, 0, e->stream>>>(p, Lout, items, count, round);
 }
 template <int LANES>
 static void launch_apply_small(Engine* e, const S2Params& p, const u32* items, u32 count)
@@ -533,25 +681,29 @@ int stage2_run(Engine* e, u32 nb, u32 E)
    p.T = e->enc; p.X = e->bt.X; p.nb = nb;
    p.sa = e->sa; p.rank = e->rank; p.nrank = e->nrank;
    p.keyA = e->keyA; p.keyB = e->keyB; p.idxB = e->idxB;
-   p.hist = e->hist; p.blockmap = e->blockmap;
+   p.hist = e->hist; p.hist_stride = e->hist_stride; p.code = e->code; p.kk = e->kk; p.nbins = e->nbins;
+   p.blockmap = e->blockmap;
    p.power_q = e->bt.power_q; p.inuse = e->bt.inuse; p.ninuse = e->bt.ninuse;
 
    const u32 nchunks = (E >> 12) + 1;
    k_blockmap<<<(nchunks + 255) / 256, 256, 0, st>>>(e->bt.X, nb, e->blockmap, nchunks);     BZ_KCHECK(e);
-   BZ_CUDA(e, cudaMemsetAsync(e->hist, 0, (size_t)nb * 65536 * sizeof(u32), st));
+   BZ_CUDA(e, cudaMemsetAsync(e->hist, 0, (size_t)nb * e->hist_stride * sizeof(u32), st));
+   BZ_CUDA(e, cudaMemsetAsync(e->bt.inuse, 0, (size_t)nb * 256, st));
    BZ_CUDA(e, cudaMemsetAsync(e->bt.power_q, 0, sizeof(u32) * nb, st));
    BZ_CUDA(e, cudaMemsetAsync(e->lists.counts[0], 0, sizeof(u32) * N_CLASSES, st));
    BZ_CUDA(e, cudaMemsetAsync(e->s1_scalars + 4, 0, sizeof(u32), st));
    const u32 max_n = e->nmax + 16;
-   const dim3 gtiles((max_n + BG_TILE - 1) / BG_TILE, nb);
-   k_bigram<BG_HIST><<<gtiles, BG_THREADS, 0, st>>>(p);                                      BZ_KCHECK(e);
-   k_bigram_scan<<<nb, 1024, 0, st>>>(p);                                                    BZ_KCHECK(e);
-   k_bigram<BG_RANK><<<gtiles, BG_THREADS, 0, st>>>(p);                                      BZ_KCHECK(e);
-   k_bigram<BG_SCATTER><<<gtiles, BG_THREADS, 0, st>>>(p);                                   BZ_KCHECK(e);
-   k_seg_init<<<dim3(256, nb), 256, 0, st>>>(p, lists_dev(e, 0));                            BZ_KCHECK(e);
+   const dim3 gtiles((max_n + KG_TILE - 1) / KG_TILE, nb);
+   k_inuse<<<gtiles, KG_THREADS, 0, st>>>(p);                                                BZ_KCHECK(e);
+   k_codemap<<<nb, 256, 0, st>>>(p);                                                         BZ_KCHECK(e);
+   k_kgram<KG_HIST><<<gtiles, KG_THREADS, 0, st>>>(p);                                       BZ_KCHECK(e);
+   k_kgram_scan<<<nb, 1024, 0, st>>>(p);                                                     BZ_KCHECK(e);
+   k_kgram<KG_RANK><<<gtiles, KG_THREADS, 0, st>>>(p);                                       BZ_KCHECK(e);
+   k_kgram<KG_SCATTER><<<gtiles, KG_THREADS, 0, st>>>(p);                                    BZ_KCHECK(e);
+   k_seg_init<<<dim3((e->hist_stride + 255) / 256, nb), 256, 0, st>>>(p, lists_dev(e, 0));   BZ_KCHECK(e);
 
    int cur = 0;
-   for (u32 h = 2; ; h *= 2) {
+   for (u32 round = 0; ; round++) {
       BZ_CUDA(e, cudaMemcpyAsync(e->h_counts, e->lists.counts[cur], sizeof(u32) * (N_CLASSES), cudaMemcpyDeviceToHost, st));
       BZ_CUDA(e, cudaMemcpyAsync(e->h_scalars + 4, e->s1_scalars + 4, sizeof(u32), cudaMemcpyDeviceToHost, st));
       BZ_CUDA(e, cudaStreamSynchronize(st));
@@ -559,20 +711,20 @@ int stage2_run(Engine* e, u32 nb, u32 E)
       u32 cnt[N_CLASSES]; u64 total = 0;
       for (int c = 0; c < N_CLASSES; c++) { cnt[c] = e->h_counts[c]; total += cnt[c]; }
       if (total == 0) break;
-      if (h >= (1u << 21)) { snprintf(e->err, sizeof e->err, "prefix doubling did not terminate"); return -5; }
+      if (round > 22) { snprintf(e->err, sizeof e->err, "prefix doubling did not terminate"); return -5; }
       const int nxt = cur ^ 1;
       BZ_CUDA(e, cudaMemsetAsync(e->lists.counts[nxt], 0, sizeof(u32) * N_CLASSES, st));
       ListsDev Lout = lists_dev(e, nxt);
       u32** si = e->lists.small_items[cur];
       u64** bi = e->lists.big_items[cur];
-      if (cnt[CLS_LARGE]) k_refine_large<<<cnt[CLS_LARGE], LG_THREADS, 0, st>>>(p, Lout, bi[2], h);
-      if (cnt[CLS_MED2])  k_refine_medium<4096, 512><<<cnt[CLS_MED2], 512, 0, st>>>(p, Lout, bi[1], h);
-      if (cnt[CLS_MED1])  k_refine_medium<512, 128><<<cnt[CLS_MED1], 128, 0, st>>>(p, Lout, bi[0], h);
-      if (cnt[4]) launch_small<32>(e, p, Lout, si[4], cnt[4], h);
-      if (cnt[3]) launch_small<16>(e, p, Lout, si[3], cnt[3], h);
-      if (cnt[2]) launch_small<8>(e, p, Lout, si[2], cnt[2], h);
-      if (cnt[1]) launch_small<4>(e, p, Lout, si[1], cnt[1], h);
-      if (cnt[0]) launch_small<2>(e, p, Lout, si[0], cnt[0], h);
+      if (cnt[CLS_LARGE]) k_refine_large<<<cnt[CLS_LARGE], LG_THREADS, 0, st>>>(p, Lout, bi[2], round);
+      if (cnt[CLS_MED2])  k_refine_medium<512, 12><<<cnt[CLS_MED2], 512, 0, st>>>(p, Lout, bi[1], cnt[CLS_MED2], round);
+      if (cnt[CLS_MED1])  k_refine_medium<32, 8><<<(cnt[CLS_MED1] + 7) / 8, 256, 0, st>>>(p, Lout, bi[0], cnt[CLS_MED1], round);
+      if (cnt[4]) launch_small<32>(e, p, Lout, si[4], cnt[4], round);
+      if (cnt[3]) launch_small<16>(e, p, Lout, si[3], cnt[3], round);
+      if (cnt[2]) launch_small<8>(e, p, Lout, si[2], cnt[2], round);
+      if (cnt[1]) launch_small<4>(e, p, Lout, si[1], cnt[1], round);
+      if (cnt[0]) launch_small<2>(e, p, Lout, si[0], cnt[0], round);
       u32 nl = 0;
       for (int c = 0; c < N_CLASSES; c++) nl += cnt[c] ? 1u : 0u;
       e->launches += nl - 1;
@@ -580,7 +732,7 @@ int stage2_run(Engine* e, u32 nb, u32 E)
       BZ_KCHECK(e);
       if (cnt[CLS_LARGE]) k_apply_big<<<cnt[CLS_LARGE], 256, 0, st>>>(p, bi[2]);
       if (cnt[CLS_MED2])  k_apply_big<<<cnt[CLS_MED2], 256, 0, st>>>(p, bi[1]);
-      if (cnt[CLS_MED1])  k_apply_big<<<cnt[CLS_MED1], 256, 0, st>>>(p, bi[0]);
+      if (cnt[CLS_MED1])  k_apply_warp<<<(cnt[CLS_MED1] + 7) / 8, 256, 0, st>>>(p, bi[0], cnt[CLS_MED1]);
       if (cnt[4]) launch_apply_small<32>(e, p, si[4], cnt[4]);
       if (cnt[3]) launch_apply_small<16>(e, p, si[3], cnt[3]);
       if (cnt[2]) launch_apply_small<8>(e, p, si[2], cnt[2]);
@@ -590,7 +742,7 @@ int stage2_run(Engine* e, u32 nb, u32 E)
       BZ_KCHECK(e);
       cur = nxt;
    }
-   k_bwt_out<<<gtiles, BG_THREADS, 0, st>>>(p, e->bwt, e->bt.origptr);                       BZ_KCHECK(e);
+   k_bwt_out<<<gtiles, KG_THREADS, 0, st>>>(p, e->bwt, e->bt.origptr);                       BZ_KCHECK(e);
    return 0;
 }
 
