@@ -69,7 +69,7 @@ static void engine_free(EngineFull* e)
    for (void* p : dev) if (p) cudaFree(p);
    for (int w = 0; w < 2; w++) {
       for (int c = 0; c < N_SMALL_CLASSES; c++) if (e->lists.small_items[w][c]) cudaFree(e->lists.small_items[w][c]);
-      for (int c = 0; c < 3; c++) if (e->lists.big_items[w][c]) cudaFree(e->lists.big_items[w][c]);
+      for (int c = 0; c < N_BIG_CLASSES; c++) if (e->lists.big_items[w][c]) cudaFree(e->lists.big_items[w][c]);
    }
    if (e->h_scalars) cudaFreeHost(e->h_scalars);
    if (e->h_counts) cudaFreeHost(e->h_counts);
@@ -97,6 +97,10 @@ static int engine_new(EngineFull** out, int device, int level, size_t window_byt
       cudaDeviceProp prop;
       cudaGetDeviceProperties(&prop, device);
       e->num_sms = prop.multiProcessorCount;
+   }
+   {
+      const char* g = getenv("BZ2_B200_S2_GROUP");
+      e->s2_group = g ? (u32)atoi(g) : 0;
    }
    if (window_bytes == 0) window_bytes = (size_t)96 << 20;
    // a window must be able to hold the input of one full block of pure runs (255 -> 5 bytes)
@@ -139,10 +143,11 @@ static int engine_new(EngineFull** out, int device, int level, size_t window_byt
       ALLOC(e->bt.bits, B); ALLOC(e->bt.bitoff, B + 2);
       static const u32 minlen[N_SMALL_CLASSES] = {2, 3, 5, 9, 17};
       for (int c = 0; c < N_SMALL_CLASSES; c++) e->lists.small_cap[c] = (u32)(E / minlen[c] + 1024);
-      e->lists.big_cap[0] = (u32)(E / 33 + 1024); e->lists.big_cap[1] = (u32)(E / 257 + 1024); e->lists.big_cap[2] = (u32)(E / 4097 + 1024);
+      static const u32 bigmin[N_BIG_CLASSES] = {33, 257, 513, 1025, 2049, 4097};
+      for (int c = 0; c < N_BIG_CLASSES; c++) e->lists.big_cap[c] = (u32)(E / bigmin[c] + 1024);
       for (int w = 0; w < 2; w++) {
          for (int c = 0; c < N_SMALL_CLASSES; c++) ALLOC(e->lists.small_items[w][c], e->lists.small_cap[c]);
-         for (int c = 0; c < 3; c++) ALLOC(e->lists.big_items[w][c], e->lists.big_cap[c]);
+         for (int c = 0; c < N_BIG_CLASSES; c++) ALLOC(e->lists.big_items[w][c], e->lists.big_cap[c]);
          ALLOC(e->lists.counts[w], N_CLASSES);
       }
       e->out_cap = E + E / 32 + B * 24576 + 4096;
@@ -151,7 +156,7 @@ static int engine_new(EngineFull** out, int device, int level, size_t window_byt
    }
    {
       cudaError_t c1 = cudaMallocHost(reinterpret_cast<void**>(&e->h_scalars), 64 * sizeof(u32));
-      cudaError_t c2 = cudaMallocHost(reinterpret_cast<void**>(&e->h_counts), 16 * sizeof(u32));
+      cudaError_t c2 = cudaMallocHost(reinterpret_cast<void**>(&e->h_counts), 32 * sizeof(u32));
       cudaError_t c3 = cudaMallocHost(reinterpret_cast<void**>(&e->h_blk), (size_t)e->blk_cap * 4 * sizeof(u32) + 64);
       if (c1 != cudaSuccess || c2 != cudaSuccess || c3 != cudaSuccess) { rc = set_err(BZ2B200_ENOMEM, "pinned host allocation failed"); goto fail; }
    }

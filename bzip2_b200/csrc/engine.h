@@ -19,12 +19,15 @@
 namespace bz {
 
 constexpr int N_SMALL_CLASSES = 5;          // segment lengths 2, 3-4, 5-8, 9-16, 17-32
-constexpr int CLS_MED1 = 5;                 // 33..256  (one warp, registers)
-constexpr int CLS_MED2 = 6;                 // 257..4096 (one CTA)
-constexpr int CLS_LARGE = 7;                // > 4096
-constexpr int N_CLASSES = 8;
-constexpr u32 MED1_MAX = 256;
-constexpr u32 MED2_MAX = 4096;
+constexpr int N_BIG_CLASSES = 6;            // u64 worklists
+constexpr int CLS_W256 = 5;                 // 33..256    one warp, registers + shuffles
+constexpr int CLS_C512 = 6;                 // 257..512   CTA of 64
+constexpr int CLS_C1K = 7;                  // 513..1024  CTA of 128
+constexpr int CLS_C2K = 8;                  // 1025..2048 CTA of 256
+constexpr int CLS_C4K = 9;                  // 2049..4096 CTA of 512
+constexpr int CLS_LARGE = 10;               // > 4096     CTA of 1024, radix passes in HBM
+constexpr int N_CLASSES = 11;
+constexpr u32 MED_MAX = 4096;
 constexpr u32 MAX_BLOCKS = 4096;            // block id must fit 12 bits in a segment entry
 constexpr u32 MAX_ENC = 1u << 27;           // flat position must fit 27 bits in a small entry
 
@@ -34,10 +37,10 @@ constexpr int MTF_TILE = 1024;              // symbols per MTF tile (one warp ea
 // (pos | (len-1) << 27); medium/large hold u64 entries (pos << 32 | blk << 20 | len).
 struct SegLists {
    u32* small_items[2][N_SMALL_CLASSES];
-   u64* big_items[2][3];
+   u64* big_items[2][N_BIG_CLASSES];
    u32* counts[2];                          // [N_CLASSES] each, device
    u32  small_cap[N_SMALL_CLASSES];
-   u32  big_cap[3];
+   u32  big_cap[N_BIG_CLASSES];
 };
 
 struct BlockTables {                        // per-window block metadata (device arrays, nb+1 or nb long)
@@ -85,6 +88,7 @@ struct Engine {
    u8  *bwt, *z;
    u16 *mtfv;
    u32 *hist;
+   u32 s2_group;           // blocks sorted per BWT sub-batch (0 = whole window)
    u32 hist_stride;        // k-gram bins reserved per block (power of two, 2^16..2^18)
    u8  *code;              // [blk_cap*256]
    u32 *kk, *nbins;        // [blk_cap]

@@ -30,10 +30,10 @@ namespace bz {
 
 struct ListsDev {
    u32* small_items[N_SMALL_CLASSES];
-   u64* big_items[3];
+   u64* big_items[N_BIG_CLASSES];
    u32* counts;
    u32  small_cap[N_SMALL_CLASSES];
-   u32  big_cap[3];
+   u32  big_cap[N_BIG_CLASSES];
    u32* overflow;
 };
 
@@ -41,6 +41,7 @@ struct S2Params {
    const u8* T;
    const u32* X;
    u32 nb;
+   u32 b0;                  // first block of the sub-batch being sorted
    u32* sa; u32* rank; u32* nrank;
    u32* keyA; u32* keyB; u32* idxB;
    u32* hist;
@@ -56,9 +57,9 @@ struct S2Params {
 __device__ __forceinline__ int seg_class(u32 len)
 {
    if (len <= 32) return 31 - __clz(len - 1);
-   if (len <= MED1_MAX) return CLS_MED1;
-   if (len <= MED2_MAX) return CLS_MED2;
-   return CLS_LARGE;
+   if (len <= 256) return CLS_W256;
+   if (len > MED_MAX) return CLS_LARGE;
+   return CLS_C512 + (23 - __clz(len - 1));     // 257..512 -> +0, ..1024 -> +1, ..2048 -> +2, ..4096 -> +3
 }
 
 // All 32 lanes of the warp must call this together.
@@ -114,7 +115,7 @@ enum { KG_HIST = 0, KG_RANK = 1, KG_SCATTER = 2 };
 __global__ void __launch_bounds__(KG_THREADS) k_inuse(S2Params p)
 {
    __shared__ u32 flags[256];
-   const u32 b = blockIdx.y;
+   const u32 b = p.b0 + blockIdx.y;
    const u32 xb = p.X[b], n = p.X[b + 1] - xb;
    const u32 t0 = blockIdx.x * KG_TILE;
    if (t0 >= n) return;
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(KG_THREADS) k_inuse(S2Params p)
 __global__ void __launch_bounds__(256) k_codemap(S2Params p)
 {
    __shared__ u32 wcnt[8];
-   const u32 b = blockIdx.x, tid = threadIdx.x, w = tid >> 5, l = lane_id();
+   const u32 b = p.b0 + blockIdx.x, tid = threadIdx.x, w = tid >> 5, l = lane_id();
    const bool used = p.inuse[(size_t)b * 256 + tid] != 0;
    const u32 bal = __ballot_sync(FULL, used);
    if (l == 0) wcnt[w] = __popc(bal);
@@ -156,13 +157,13 @@ __global__ void __launch_bounds__(KG_THREADS) k_kgram(S2Params p)
 {
    __shared__ u8 sc[KG_TILE + KG_MAXK + 8];
    __shared__ u8 cmap[256];
-   const u32 b = blockIdx.y;
+   const u32 b = p.b0 + blockIdx.y;
    const u32 xb = p.X[b], n = p.X[b + 1] - xb;
    const u32 t0 = blockIdx.x * KG_TILE;
    if (t0 >= n) return;
    const u8* T = p.T + xb;
    const u32 k = p.kk[b], base = p.ninuse[b];
-   u32* hist = p.hist + (size_t)b * p.hist_stride;
+   u32* hist = p.hist + (size_t)(b - p.b0) * p.hist_stride;
    cmap[threadIdx.x] = p.code[(size_t)b * 256 + threadIdx.x];
    __syncthreads();
    const u32 span = min((u32)KG_TILE, n - t0) + k - 1;
@@ -191,8 +192,8 @@ __global__ void __launch_bounds__(1024) k_kgram_scan(S2Params p)
 {
    __shared__ u32 ssm[34];
    __shared__ u32 s_run;
-   const u32 b = blockIdx.x;
-   u32* hist = p.hist + (size_t)b * p.hist_stride;
+   const u32 b = p.b0 + blockIdx.x;
+   u32* hist = p.hist + (size_t)(b - p.b0) * p.hist_stride;
    const u32 nbins = p.nbins[b];
    if (threadIdx.x == 0) s_run = 0;
    __syncthreads();
@@ -222,9 +223,9 @@ __global__ void __launch_bounds__(1024) k_kgram_scan(S2Params p)
 // after the scatter hist[bin] is the END of bucket `bin`; emit the initial segments
 __global__ void __launch_bounds__(256) k_seg_init(S2Params p, ListsDev L)
 {
-   const u32 b = blockIdx.y;
+   const u32 b = p.b0 + blockIdx.y;
    const u32 xb = p.X[b], n = p.X[b + 1] - xb;
-   const u32* hist = p.hist + (size_t)b * p.hist_stride;
+   const u32* hist = p.hist + (size_t)(b - p.b0) * p.hist_stride;
    const u32 bin = blockIdx.x * 256 + threadIdx.x;
    const bool vbin = bin < p.nbins[b];
    const u32 end = vbin ? hist[bin] : 0;
@@ -625,13 +626,13 @@ __global__ void __launch_bounds__(256) k_apply_big(S2Params p, const u64* items)
    const u32 b = (u32)(entry >> 20) & 0xfffu;
    const u32 len = (u32)entry & 0xfffffu;
    const u32 xb = p.X[b];
-   for (u32 i = threadIdx.x; i < len; i += 256) p.rank[xb + p.sa[pos + i]] = p.nrank[pos + i];
+   for (u32 i = threadIdx.x; i < len; i += blockDim.x) p.rank[xb + p.sa[pos + i]] = p.nrank[pos + i];
 }
 
 // ---- 3. last column -------------------------------------------------------------------
 __global__ void __launch_bounds__(KG_THREADS) k_bwt_out(S2Params p, u8* bwt, u32* origptr)
 {
-   const u32 b = blockIdx.y;
+   const u32 b = p.b0 + blockIdx.y;
    const u32 xb = p.X[b], n = p.X[b + 1] - xb;
    const u32 t0 = blockIdx.x * KG_TILE;
    if (t0 >= n) return;
@@ -653,7 +654,7 @@ static ListsDev lists_dev(Engine* e, int which)
 {
    ListsDev L;
    for (int c = 0; c < N_SMALL_CLASSES; c++) { L.small_items[c] = e->lists.small_items[which][c]; L.small_cap[c] = e->lists.small_cap[c]; }
-   for (int c = 0; c < 3; c++) { L.big_items[c] = e->lists.big_items[which][c]; L.big_cap[c] = e->lists.big_cap[c]; }
+   for (int c = 0; c < N_BIG_CLASSES; c++) { L.big_items[c] = e->lists.big_items[which][c]; L.big_cap[c] = e->lists.big_cap[c]; }
    L.counts = e->lists.counts[which];
    L.overflow = e->s1_scalars + 4;
    return L;
@@ -687,62 +688,74 @@ int stage2_run(Engine* e, u32 nb, u32 E)
 
    const u32 nchunks = (E >> 12) + 1;
    k_blockmap<<<(nchunks + 255) / 256, 256, 0, st>>>(e->bt.X, nb, e->blockmap, nchunks);     BZ_KCHECK(e);
-   BZ_CUDA(e, cudaMemsetAsync(e->hist, 0, (size_t)nb * e->hist_stride * sizeof(u32), st));
    BZ_CUDA(e, cudaMemsetAsync(e->bt.inuse, 0, (size_t)nb * 256, st));
    BZ_CUDA(e, cudaMemsetAsync(e->bt.power_q, 0, sizeof(u32) * nb, st));
-   BZ_CUDA(e, cudaMemsetAsync(e->lists.counts[0], 0, sizeof(u32) * N_CLASSES, st));
    BZ_CUDA(e, cudaMemsetAsync(e->s1_scalars + 4, 0, sizeof(u32), st));
    const u32 max_n = e->nmax + 16;
-   const dim3 gtiles((max_n + KG_TILE - 1) / KG_TILE, nb);
-   k_inuse<<<gtiles, KG_THREADS, 0, st>>>(p);                                                BZ_KCHECK(e);
-   k_codemap<<<nb, 256, 0, st>>>(p);                                                         BZ_KCHECK(e);
-   k_kgram<KG_HIST><<<gtiles, KG_THREADS, 0, st>>>(p);                                       BZ_KCHECK(e);
-   k_kgram_scan<<<nb, 1024, 0, st>>>(p);                                                     BZ_KCHECK(e);
-   k_kgram<KG_RANK><<<gtiles, KG_THREADS, 0, st>>>(p);                                       BZ_KCHECK(e);
-   k_kgram<KG_SCATTER><<<gtiles, KG_THREADS, 0, st>>>(p);                                    BZ_KCHECK(e);
-   k_seg_init<<<dim3((e->hist_stride + 255) / 256, nb), 256, 0, st>>>(p, lists_dev(e, 0));   BZ_KCHECK(e);
+   // Blocks are sorted in sub-batches small enough for their rank/sa arrays to stay in L2.
+   const u32 group = e->s2_group ? e->s2_group : nb;
+   for (u32 b0 = 0; b0 < nb; b0 += group) {
+      const u32 g = (nb - b0 < group) ? (nb - b0) : group;
+      p.b0 = b0;
+      BZ_CUDA(e, cudaMemsetAsync(e->hist, 0, (size_t)g * e->hist_stride * sizeof(u32), st));
+      BZ_CUDA(e, cudaMemsetAsync(e->lists.counts[0], 0, sizeof(u32) * N_CLASSES, st));
+      const dim3 gtiles((max_n + KG_TILE - 1) / KG_TILE, g);
+      k_inuse<<<gtiles, KG_THREADS, 0, st>>>(p);                                                BZ_KCHECK(e);
+      k_codemap<<<g, 256, 0, st>>>(p);                                                          BZ_KCHECK(e);
+      k_kgram<KG_HIST><<<gtiles, KG_THREADS, 0, st>>>(p);                                       BZ_KCHECK(e);
+      k_kgram_scan<<<g, 1024, 0, st>>>(p);                                                      BZ_KCHECK(e);
+      k_kgram<KG_RANK><<<gtiles, KG_THREADS, 0, st>>>(p);                                       BZ_KCHECK(e);
+      k_kgram<KG_SCATTER><<<gtiles, KG_THREADS, 0, st>>>(p);                                    BZ_KCHECK(e);
+      k_seg_init<<<dim3((e->hist_stride + 255) / 256, g), 256, 0, st>>>(p, lists_dev(e, 0));    BZ_KCHECK(e);
 
-   int cur = 0;
-   for (u32 round = 0; ; round++) {
-      BZ_CUDA(e, cudaMemcpyAsync(e->h_counts, e->lists.counts[cur], sizeof(u32) * (N_CLASSES), cudaMemcpyDeviceToHost, st));
-      BZ_CUDA(e, cudaMemcpyAsync(e->h_scalars + 4, e->s1_scalars + 4, sizeof(u32), cudaMemcpyDeviceToHost, st));
-      BZ_CUDA(e, cudaStreamSynchronize(st));
-      if (e->h_scalars[4]) { snprintf(e->err, sizeof e->err, "segment worklist overflow"); return -4; }
-      u32 cnt[N_CLASSES]; u64 total = 0;
-      for (int c = 0; c < N_CLASSES; c++) { cnt[c] = e->h_counts[c]; total += cnt[c]; }
-      if (total == 0) break;
-      if (round > 22) { snprintf(e->err, sizeof e->err, "prefix doubling did not terminate"); return -5; }
-      const int nxt = cur ^ 1;
-      BZ_CUDA(e, cudaMemsetAsync(e->lists.counts[nxt], 0, sizeof(u32) * N_CLASSES, st));
-      ListsDev Lout = lists_dev(e, nxt);
-      u32** si = e->lists.small_items[cur];
-      u64** bi = e->lists.big_items[cur];
-      if (cnt[CLS_LARGE]) k_refine_large<<<cnt[CLS_LARGE], LG_THREADS, 0, st>>>(p, Lout, bi[2], round);
-      if (cnt[CLS_MED2])  k_refine_medium<512, 12><<<cnt[CLS_MED2], 512, 0, st>>>(p, Lout, bi[1], cnt[CLS_MED2], round);
-      if (cnt[CLS_MED1])  k_refine_medium<32, 8><<<(cnt[CLS_MED1] + 7) / 8, 256, 0, st>>>(p, Lout, bi[0], cnt[CLS_MED1], round);
-      if (cnt[4]) launch_small<32>(e, p, Lout, si[4], cnt[4], round);
-      if (cnt[3]) launch_small<16>(e, p, Lout, si[3], cnt[3], round);
-      if (cnt[2]) launch_small<8>(e, p, Lout, si[2], cnt[2], round);
-      if (cnt[1]) launch_small<4>(e, p, Lout, si[1], cnt[1], round);
-      if (cnt[0]) launch_small<2>(e, p, Lout, si[0], cnt[0], round);
-      u32 nl = 0;
-      for (int c = 0; c < N_CLASSES; c++) nl += cnt[c] ? 1u : 0u;
-      e->launches += nl - 1;
-      e->bwt_rounds++;
-      BZ_KCHECK(e);
-      if (cnt[CLS_LARGE]) k_apply_big<<<cnt[CLS_LARGE], 256, 0, st>>>(p, bi[2]);
-      if (cnt[CLS_MED2])  k_apply_big<<<cnt[CLS_MED2], 256, 0, st>>>(p, bi[1]);
-      if (cnt[CLS_MED1])  k_apply_warp<<<(cnt[CLS_MED1] + 7) / 8, 256, 0, st>>>(p, bi[0], cnt[CLS_MED1]);
-      if (cnt[4]) launch_apply_small<32>(e, p, si[4], cnt[4]);
-      if (cnt[3]) launch_apply_small<16>(e, p, si[3], cnt[3]);
-      if (cnt[2]) launch_apply_small<8>(e, p, si[2], cnt[2]);
-      if (cnt[1]) launch_apply_small<4>(e, p, si[1], cnt[1]);
-      if (cnt[0]) launch_apply_small<2>(e, p, si[0], cnt[0]);
-      e->launches += nl - 1;
-      BZ_KCHECK(e);
-      cur = nxt;
+      int cur = 0;
+      for (u32 round = 0; ; round++) {
+         BZ_CUDA(e, cudaMemcpyAsync(e->h_counts, e->lists.counts[cur], sizeof(u32) * (N_CLASSES), cudaMemcpyDeviceToHost, st));
+         BZ_CUDA(e, cudaMemcpyAsync(e->h_scalars + 4, e->s1_scalars + 4, sizeof(u32), cudaMemcpyDeviceToHost, st));
+         BZ_CUDA(e, cudaStreamSynchronize(st));
+         if (e->h_scalars[4]) { snprintf(e->err, sizeof e->err, "segment worklist overflow"); return -4; }
+         u32 cnt[N_CLASSES]; u64 total = 0;
+         for (int c = 0; c < N_CLASSES; c++) { cnt[c] = e->h_counts[c]; total += cnt[c]; }
+         if (total == 0) break;
+         if (round > 22) { snprintf(e->err, sizeof e->err, "prefix doubling did not terminate"); return -5; }
+         const int nxt = cur ^ 1;
+         BZ_CUDA(e, cudaMemsetAsync(e->lists.counts[nxt], 0, sizeof(u32) * N_CLASSES, st));
+         ListsDev Lout = lists_dev(e, nxt);
+         u32** si = e->lists.small_items[cur];
+         u64** bi = e->lists.big_items[cur];
+         if (cnt[CLS_LARGE]) k_refine_large<<<cnt[CLS_LARGE], LG_THREADS, 0, st>>>(p, Lout, bi[5], round);
+         if (cnt[CLS_C4K])   k_refine_medium<512, 12><<<cnt[CLS_C4K], 512, 0, st>>>(p, Lout, bi[4], cnt[CLS_C4K], round);
+         if (cnt[CLS_C2K])   k_refine_medium<256, 12><<<cnt[CLS_C2K], 256, 0, st>>>(p, Lout, bi[3], cnt[CLS_C2K], round);
+         if (cnt[CLS_C1K])   k_refine_medium<128, 12><<<cnt[CLS_C1K], 128, 0, st>>>(p, Lout, bi[2], cnt[CLS_C1K], round);
+         if (cnt[CLS_C512])  k_refine_medium<64, 12><<<cnt[CLS_C512], 64, 0, st>>>(p, Lout, bi[1], cnt[CLS_C512], round);
+         if (cnt[CLS_W256])  k_refine_medium<32, 8><<<(cnt[CLS_W256] + 7) / 8, 256, 0, st>>>(p, Lout, bi[0], cnt[CLS_W256], round);
+         if (cnt[4]) launch_small<32>(e, p, Lout, si[4], cnt[4], round);
+         if (cnt[3]) launch_small<16>(e, p, Lout, si[3], cnt[3], round);
+         if (cnt[2]) launch_small<8>(e, p, Lout, si[2], cnt[2], round);
+         if (cnt[1]) launch_small<4>(e, p, Lout, si[1], cnt[1], round);
+         if (cnt[0]) launch_small<2>(e, p, Lout, si[0], cnt[0], round);
+         u32 nl = 0;
+         for (int c = 0; c < N_CLASSES; c++) nl += cnt[c] ? 1u : 0u;
+         e->launches += nl - 1;
+         e->bwt_rounds++;
+         BZ_KCHECK(e);
+         if (cnt[CLS_LARGE]) k_apply_big<<<cnt[CLS_LARGE], 256, 0, st>>>(p, bi[5]);
+         if (cnt[CLS_C4K])   k_apply_big<<<cnt[CLS_C4K], 256, 0, st>>>(p, bi[4]);
+         if (cnt[CLS_C2K])   k_apply_big<<<cnt[CLS_C2K], 256, 0, st>>>(p, bi[3]);
+         if (cnt[CLS_C1K])   k_apply_big<<<cnt[CLS_C1K], 128, 0, st>>>(p, bi[2]);
+         if (cnt[CLS_C512])  k_apply_big<<<cnt[CLS_C512], 64, 0, st>>>(p, bi[1]);
+         if (cnt[CLS_W256])  k_apply_warp<<<(cnt[CLS_W256] + 7) / 8, 256, 0, st>>>(p, bi[0], cnt[CLS_W256]);
+         if (cnt[4]) launch_apply_small<32>(e, p, si[4], cnt[4]);
+         if (cnt[3]) launch_apply_small<16>(e, p, si[3], cnt[3]);
+         if (cnt[2]) launch_apply_small<8>(e, p, si[2], cnt[2]);
+         if (cnt[1]) launch_apply_small<4>(e, p, si[1], cnt[1]);
+         if (cnt[0]) launch_apply_small<2>(e, p, si[0], cnt[0]);
+         e->launches += nl - 1;
+         BZ_KCHECK(e);
+         cur = nxt;
+      }
+      k_bwt_out<<<gtiles, KG_THREADS, 0, st>>>(p, e->bwt, e->bt.origptr);                       BZ_KCHECK(e);
    }
-   k_bwt_out<<<gtiles, KG_THREADS, 0, st>>>(p, e->bwt, e->bt.origptr);                       BZ_KCHECK(e);
    return 0;
 }
 

@@ -6,12 +6,11 @@
 //                               effect of a tile on the MTF list is "move these to the
 //                               front in this order", which composes left to right.
 //   k_mtf_lists    (CTA/block)  folds the summaries, storing the list each tile starts with
-//   k_mtf_encode   (warp/tile)  the real MTF: the list lives in registers (8 bytes per
-//                               lane); a symbol is located with a SWAR byte compare and a
-//                               ballot, and rotated to the front with one shuffle.
-//   k_rle2_count / k_rle2_scan / k_rle2_emit
-//                               zero runs are counted per tile, runs crossing tiles are
-//                               stitched by a per-block scan, then symbols are written at
+//   k_mtf_encode   (thread/tile) the real MTF with the tile's list in shared memory (column
+//                               layout, one column per thread); 32 tiles advance per warp
+//                               instruction.  Also records the tile's zero-run shape.
+//   k_rle2_scan / k_rle2_emit   runs crossing tiles are stitched by a per-block warp scan of
+//                               (lead, trail, inner) summaries, then symbols are written at
 //                               their final offsets and mtfFreq is accumulated.
 // Output per block: mtfv[] (u16), nMTF, mtfFreq[258]; symbol values as in the reference
 // (RUNA=0, RUNB=1, position p>0 -> p+1, EOB = nInUse+1).
@@ -117,72 +116,90 @@ __global__ void __launch_bounds__(256) k_mtf_lists(S3Params p)
    }
 }
 
-__global__ void __launch_bounds__(256) k_mtf_encode(S3Params p)
-{
-   const u32 w = threadIdx.x >> 5, l = lane_id();
-   const u32 b = blockIdx.y;
-   const u32 t = blockIdx.x * 8 + w;
-   const u32 xb = p.X[b], n = p.X[b + 1] - xb;
-   if ((u64)t * MTF_TILE >= n) return;
-   const u32 start = xb + t * MTF_TILE;
-   const u32 size = min((u32)MTF_TILE, n - t * MTF_TILE);
-   u64 L = reinterpret_cast<const u64*>(p.lists + ((size_t)b * p.tiles_max + t) * 256)[l];
-   u32 front = __shfl_sync(FULL, (u32)(L & 0xff), 0);
-   for (u32 base = 0; base < size; base += 32) {
-      const u32 i = base + l;
-      const u32 sym = (i < size) ? p.bwt[start + i] : 0;
-      const u32 cntj = min(32u, size - base);
-      u32 myz = 0;
-      for (u32 j = 0; j < cntj; j++) {
-         const u32 c = __shfl_sync(FULL, sym, j);
-         u32 pos = 0;
-         if (c != front) {
-            const u64 x = L ^ (0x0101010101010101ULL * (u64)c);
-            const u64 zm = (x - 0x0101010101010101ULL) & ~x & 0x8080808080808080ULL;
-            const u32 hit = __ballot_sync(FULL, zm != 0);
-            if (hit) {
-               const u32 f = __ffs(hit) - 1;
-               u32 bi = zm ? (u32)((__ffsll((long long)zm) - 1) >> 3) : 0;
-               bi = __shfl_sync(FULL, bi, f);
-               pos = f * 8 + bi;
-               u32 top = __shfl_up_sync(FULL, (u32)(L >> 56), 1);
-               if (l == 0) top = c;
-               if (l < f) L = (L << 8) | (u64)top;
-               else if (l == f) {
-                  const u64 lowmask = bi ? ((1ULL << (8 * bi)) - 1ULL) : 0ULL;
-                  const u64 keepmask = (bi == 7) ? 0ULL : ~((1ULL << (8 * (bi + 1))) - 1ULL);
-                  L = (L & keepmask) | ((L & lowmask) << 8) | (u64)top;
-               }
-               front = c;
-            }
-         }
-         if (l == j) myz = pos;
-      }
-      if (i < size) p.z[start + i] = (u8)myz;
-   }
-}
-
 __device__ __forceinline__ u32 run_digits(u32 r) { return 31 - __clz(r + 1); }
 
-// one thread per tile: zero-run shape of the tile
-__global__ void __launch_bounds__(128) k_rle2_count(S3Params p)
+// One THREAD per tile.  The 256-entry list of thread t lives in shared memory at
+// lst[j * MTF_CTA + t] (conflict-free for any mix of j across lanes).  All tiles of a block
+// share the same misalignment, so the tile is read as aligned 32-bit words without divergence.
+// Also records the zero-run shape of the tile (lead / trail / inner symbol count) for RLE2.
+constexpr int MTF_CTA = 128;
+
+__global__ void __launch_bounds__(MTF_CTA) k_mtf_encode(S3Params p)
 {
+   __shared__ u8 lst[256 * MTF_CTA];
    const u32 b = blockIdx.y;
-   const u32 t = blockIdx.x * 128 + threadIdx.x;
+   const u32 tid = threadIdx.x;
+   const u32 t = blockIdx.x * MTF_CTA + tid;
    const u32 xb = p.X[b], n = p.X[b + 1] - xb;
-   if ((u64)t * MTF_TILE >= n) return;
+   const u32 ntile = (n + MTF_TILE - 1) / MTF_TILE;
+   const u32 t0 = blockIdx.x * MTF_CTA;
+   if (t0 >= ntile) return;
+   // stage the start lists of this CTA's tiles (coalesced 256-byte rows -> interleaved columns)
+   {
+      const u8* src = p.lists + ((size_t)b * p.tiles_max + t0) * 256;
+      const u32 nt = min((u32)MTF_CTA, ntile - t0);
+      for (u32 q = tid; q < nt * 64; q += MTF_CTA) {
+         const u32 tile = q % nt, w = q / nt;       // lanes vary in tile: conflict-free shared-memory columns
+         const u32 v = reinterpret_cast<const u32*>(src)[tile * 64 + w];
+         lst[(w * 4 + 0) * MTF_CTA + tile] = (u8)v;
+         lst[(w * 4 + 1) * MTF_CTA + tile] = (u8)(v >> 8);
+         lst[(w * 4 + 2) * MTF_CTA + tile] = (u8)(v >> 16);
+         lst[(w * 4 + 3) * MTF_CTA + tile] = (u8)(v >> 24);
+      }
+   }
+   __syncthreads();
+   if (t >= ntile) return;
    const u32 start = xb + t * MTF_TILE;
    const u32 size = min((u32)MTF_TILE, n - t * MTF_TILE);
+   const u32 a = start & 3u;
+   const u32* in32 = reinterpret_cast<const u32*>(p.bwt + (start - a));
+   u32* out32 = reinterpret_cast<u32*>(p.z + (start - a));
+   u8* my = lst + tid;
+   u32 front = my[0];
    u32 lead = 0, run = 0, inner = 0;
    bool seen_nz = false;
-   for (u32 i = 0; i < size; i++) {
-      const u32 v = p.z[start + i];
-      if (v == 0) run++;
+   const u32 nwords = (size + a + 3) >> 2;
+   for (u32 w = 0; w < nwords; w++) {
+      const u32 word = in32[w];
+      u32 zword = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+         const i32 i = (i32)(w * 4 + k) - (i32)a;
+         if (i < 0 || i >= (i32)size) continue;
+         const u32 c = (word >> (8 * k)) & 0xff;
+         u32 pos = 0;
+         if (c != front) {
+            u32 prev = front;
+            u32 j = 1;
+            for (;;) {
+               const u32 cur = my[j * MTF_CTA];
+               my[j * MTF_CTA] = (u8)prev;
+               if (cur == c) break;
+               prev = cur;
+               j++;
+            }
+            my[0] = (u8)c;
+            front = c;
+            pos = j;
+         }
+         zword |= pos << (8 * k);
+         if (pos == 0) run++;
+         else {
+            if (!seen_nz) { lead = run; seen_nz = true; }
+            else if (run) inner += run_digits(run);
+            inner += 1;
+            run = 0;
+         }
+      }
+      // interior words are owned by this tile; edge words are shared with the neighbours
+      const bool full = (w * 4 >= a) && (w * 4 + 4 <= a + size);
+      if (full) out32[w] = zword;
       else {
-         if (!seen_nz) { lead = run; seen_nz = true; }
-         else if (run) inner += run_digits(run);
-         inner += 1;
-         run = 0;
+#pragma unroll
+         for (int k = 0; k < 4; k++) {
+            const i32 i = (i32)(w * 4 + k) - (i32)a;
+            if (i >= 0 && i < (i32)size) p.z[start + i] = (u8)(zword >> (8 * k));
+         }
       }
    }
    u32* m = p.tmeta + ((size_t)b * p.tiles_max + t) * 4;
@@ -190,29 +207,71 @@ __global__ void __launch_bounds__(128) k_rle2_count(S3Params p)
    else { m[0] = lead; m[1] = run; m[2] = inner; }
 }
 
-// one thread per block: stitch runs across tiles, assign output offsets, nMTF
-__global__ void k_rle2_scan(S3Params p, u32 nb)
+// Zero-run stitching across tiles: one WARP per block.  A range of tiles is summarised as
+// (all-zero?, leading zeros, trailing zeros, symbols emitted after the leading run), which
+// composes associatively, so the carry into every tile is an exclusive scan.
+struct RunSum { u32 allz, lead, trail, inner; };
+__device__ __forceinline__ RunSum rs_comb(RunSum A, RunSum B)
 {
-   const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+   RunSum r;
+   if (A.allz) { r = B; r.lead = A.lead + B.lead; if (B.allz) r.trail = r.lead; return r; }
+   if (B.allz) { r = A; r.trail = A.trail + B.lead; return r; }
+   const u32 mid = A.trail + B.lead;
+   r.allz = 0; r.lead = A.lead; r.trail = B.trail;
+   r.inner = A.inner + B.inner + (mid ? run_digits(mid) : 0);
+   return r;
+}
+__device__ __forceinline__ RunSum rs_load(const u32* m)
+{
+   RunSum r;
+   const u32 tr = m[1];
+   r.allz = tr >> 31; r.lead = m[0]; r.trail = tr & 0x7fffffffu; r.inner = m[2];
+   return r;
+}
+
+constexpr int RS_PER_LANE = 32;            // up to 1024 tiles per block
+
+__global__ void __launch_bounds__(256) k_rle2_scan(S3Params p, u32 nb)
+{
+   const u32 b = blockIdx.x * 8 + (threadIdx.x >> 5);
    if (b >= nb) return;
+   const u32 l = lane_id();
    const u32 n = p.X[b + 1] - p.X[b];
    const u32 ntile = (n + MTF_TILE - 1) / MTF_TILE;
+   const u32 per = (ntile + 31) / 32;
    u32* m = p.tmeta + (size_t)b * p.tiles_max * 4;
    u32* cy = p.tcarry + (size_t)b * p.tiles_max;
-   u32 carry = 0, o = 0;
-   for (u32 t = 0; t < ntile; t++) {
-      cy[t] = carry;
-      m[4 * t + 3] = o;
-      const u32 trail = m[4 * t + 1];
-      if (trail & 0x80000000u) carry += (trail & 0x7fffffffu);
-      else {
-         const u32 r = carry + m[4 * t];
-         o += m[4 * t + 2] + (r ? run_digits(r) : 0);
-         carry = trail;
-      }
+   const RunSum ident = {1u, 0u, 0u, 0u};
+   RunSum mine = ident;
+   const u32 lo = l * per;
+   for (u32 k = 0; k < per; k++) if (lo + k < ntile) mine = rs_comb(mine, rs_load(m + 4 * (lo + k)));
+   // inclusive warp scan
+   RunSum inc = mine;
+#pragma unroll
+   for (int d = 1; d < 32; d <<= 1) {
+      RunSum o;
+      o.allz = __shfl_up_sync(FULL, inc.allz, d); o.lead = __shfl_up_sync(FULL, inc.lead, d);
+      o.trail = __shfl_up_sync(FULL, inc.trail, d); o.inner = __shfl_up_sync(FULL, inc.inner, d);
+      if (l >= (u32)d) inc = rs_comb(o, inc);
    }
-   if (carry) o += run_digits(carry);
-   p.nmtf[b] = o + 1;                       // + EOB
+   RunSum pre;
+   pre.allz = __shfl_up_sync(FULL, inc.allz, 1); pre.lead = __shfl_up_sync(FULL, inc.lead, 1);
+   pre.trail = __shfl_up_sync(FULL, inc.trail, 1); pre.inner = __shfl_up_sync(FULL, inc.inner, 1);
+   if (l == 0) pre = ident;
+   for (u32 k = 0; k < per; k++) {
+      const u32 t = lo + k;
+      if (t >= ntile) break;
+      cy[t] = pre.allz ? pre.lead : pre.trail;                                     // zero run entering tile t
+      m[4 * t + 3] = pre.allz ? 0u : (pre.inner + (pre.lead ? run_digits(pre.lead) : 0u));   // symbols emitted before it
+      pre = rs_comb(pre, rs_load(m + 4 * t));
+   }
+   if (l == 31) {
+      // `inc` of the last lane covers the whole block
+      u32 o;
+      if (inc.allz) o = run_digits(inc.lead);
+      else o = inc.inner + (inc.lead ? run_digits(inc.lead) : 0u) + (inc.trail ? run_digits(inc.trail) : 0u);
+      p.nmtf[b] = o + 1;                   // + EOB
+   }
 }
 
 __global__ void __launch_bounds__(128) k_rle2_emit(S3Params p)
@@ -272,9 +331,8 @@ int stage3_run(Engine* e, u32 nb, u32 E)
    const dim3 gt((tiles_max + 127) / 128, nb);
    k_mtf_summary<<<gw, 256, 0, st>>>(p);                BZ_KCHECK(e);
    k_mtf_lists<<<nb, 256, 0, st>>>(p);                  BZ_KCHECK(e);
-   k_mtf_encode<<<gw, 256, 0, st>>>(p);                 BZ_KCHECK(e);
-   k_rle2_count<<<gt, 128, 0, st>>>(p);                 BZ_KCHECK(e);
-   k_rle2_scan<<<(nb + 63) / 64, 64, 0, st>>>(p, nb);   BZ_KCHECK(e);
+   k_mtf_encode<<<gt, MTF_CTA, 0, st>>>(p);             BZ_KCHECK(e);
+   k_rle2_scan<<<(nb + 7) / 8, 256, 0, st>>>(p, nb);    BZ_KCHECK(e);
    k_rle2_emit<<<gt, 128, 0, st>>>(p);                  BZ_KCHECK(e);
    return 0;
 }
