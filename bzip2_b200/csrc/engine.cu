@@ -60,7 +60,7 @@ static void engine_free(EngineFull* e)
 {
    if (!e) return;
    cudaSetDevice(e->device);
-   void* dev[] = { e->enc, e->cend, e->sa, e->rank, e->nrank, e->keyA, e->keyB, e->idxB, e->bwt, e->z, e->mtfv, e->hist,
+   void* dev[] = { e->enc, e->cend, e->sa, e->rank, e->keyA, e->keyB, e->idxB, e->bwt, e->z, e->mtfv, e->hist,
                    e->blockmap, e->code, e->kk, e->nbins, e->tile_len, e->tile_ext, e->tile_carry, e->tile_size, e->tile_base, e->s1_scalars,
                    e->mtf_summary, e->mtf_tilemeta, e->mtf_tilecnt, e->sel, e->hlen, e->hfreq, e->hcode, e->grpbits,
                    e->pre, e->prebits, e->ngroups, e->d_in, e->d_out,
@@ -120,7 +120,7 @@ static int engine_new(EngineFull** out, int device, int level, size_t window_byt
       e->stream = e->own_stream;
       for (int i = 0; i < 6; i++) cudaEventCreate(&e->ev[i]);
       ALLOC(e->enc, E + 64); ALLOC(e->cend, E + 64);
-      ALLOC(e->sa, E + 64); ALLOC(e->rank, E + 64); ALLOC(e->nrank, E + 64);
+      ALLOC(e->sa, E + 64); ALLOC(e->rank, E + 64);
       ALLOC(e->keyA, E + 64); ALLOC(e->keyB, E + 64); ALLOC(e->idxB, E + 64);
       ALLOC(e->bwt, E + 64); ALLOC(e->z, E + 64); ALLOC(e->mtfv, E + B + 64);
       e->hist_stride = 1u << 16;
@@ -303,6 +303,13 @@ static int begin_stream(EngineFull* e, Sink& sk)
    return host_put_bits(e, sk, 0x425A6830u + (u32)e->level, 32);            // compress.c:841-845  "BZh" '0'+level
 }
 
+// Makes the engine's device current for the duration of a C-ABI call and restores the caller's.
+struct DeviceGuard {
+   int prev;
+   explicit DeviceGuard(int dev) : prev(-1) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 } // namespace bz
 
 using namespace bz;
@@ -322,8 +329,11 @@ int bz2b200_device_count(void)
 int bz2b200_engine_create(bz2b200_engine** out, int device, int block_size_100k, size_t window_bytes)
 {
    if (!out) return set_err(BZ2B200_EPARAM, "null out pointer");
+   int prev = -1;
+   cudaGetDevice(&prev);
    EngineFull* e = nullptr;
    int rc = engine_new(&e, device, block_size_100k, window_bytes);
+   if (prev >= 0) cudaSetDevice(prev);
    if (rc) return rc;
    stream_reset(e);
    *out = reinterpret_cast<bz2b200_engine*>(e);
@@ -332,6 +342,8 @@ int bz2b200_engine_create(bz2b200_engine** out, int device, int block_size_100k,
 
 void bz2b200_engine_destroy(bz2b200_engine* h)
 {
+   if (!h) return;
+   DeviceGuard guard(reinterpret_cast<EngineFull*>(h)->device);
    engine_free(reinterpret_cast<EngineFull*>(h));
 }
 
@@ -340,7 +352,7 @@ int bz2b200_compress_host(bz2b200_engine* h, const void* src, size_t src_len, vo
 {
    EngineFull* e = reinterpret_cast<EngineFull*>(h);
    if (!e || !dst || !dst_len || (!src && src_len)) return set_err(BZ2B200_EPARAM, "bad argument");
-   cudaSetDevice(e->device);
+   DeviceGuard guard(e->device);
    int rc = ensure_staging(e, false);
    if (rc) return rc;
    stream_reset(e);
@@ -371,7 +383,7 @@ int bz2b200_compress_device(bz2b200_engine* h, const void* d_src, size_t src_len
 {
    EngineFull* e = reinterpret_cast<EngineFull*>(h);
    if (!e || !d_dst || !dst_len || (!d_src && src_len) || ((uintptr_t)d_dst & 3)) return set_err(BZ2B200_EPARAM, "bad argument");
-   cudaSetDevice(e->device);
+   DeviceGuard guard(e->device);
    stream_reset(e);
    StreamState& ss = e->ss;
    u8* out = static_cast<u8*>(d_dst);
@@ -409,7 +421,7 @@ int bz2b200_stream_begin(bz2b200_engine* h)
 {
    EngineFull* e = reinterpret_cast<EngineFull*>(h);
    if (!e) return set_err(BZ2B200_EPARAM, "null engine");
-   cudaSetDevice(e->device);
+   DeviceGuard guard(e->device);
    int rc = ensure_staging(e, true);
    if (rc) return rc;
    stream_reset(e);
@@ -421,7 +433,7 @@ int bz2b200_stream_feed(bz2b200_engine* h, const void* src, size_t n, int end_mo
    EngineFull* e = reinterpret_cast<EngineFull*>(h);
    if (!e || !sink || (!src && n) || end_mode < 0 || end_mode > 2) return set_err(BZ2B200_EPARAM, "bad argument");
    if (!e->h_in) return set_err(BZ2B200_EPARAM, "bz2b200_stream_begin was not called");
-   cudaSetDevice(e->device);
+   DeviceGuard guard(e->device);
    StreamState& ss = e->ss;
    Sink sk; sk.fn = sink; sk.user = user; sk.dst = nullptr; sk.cap = 0; sk.len = 0;
    int rc;
@@ -474,7 +486,7 @@ int bz2b200_debug_fetch(bz2b200_engine* h, const char* name, void* dst, size_t c
 {
    EngineFull* e = reinterpret_cast<EngineFull*>(h);
    if (!e || !name || !dst || !got) return set_err(BZ2B200_EPARAM, "bad argument");
-   cudaSetDevice(e->device);
+   DeviceGuard guard(e->device);
    const size_t nb = e->last_nb, E = e->last_E;
    const void* src = nullptr; size_t bytes = 0;
    struct { const char* n; const void* p; size_t b; } tab[] = {
@@ -483,7 +495,7 @@ int bz2b200_debug_fetch(bz2b200_engine* h, const char* name, void* dst, size_t c
       {"ninuse", e->bt.ninuse, nb * 4}, {"nmtf", e->bt.nmtf, nb * 4}, {"mtffreq", e->bt.mtffreq, nb * BZ_MAX_ALPHA * 4},
       {"bits", e->bt.bits, nb * 8}, {"bitoff", e->bt.bitoff, (nb + 1) * 8},
       {"enc", e->enc, E}, {"bwt", e->bwt, E}, {"z", e->z, E}, {"mtfv", e->mtfv, (E + nb) * 2}, {"sa", e->sa, E * 4},
-      {"rank", e->rank, E * 4},
+      {"rank", e->rank, E * 8},
       {"sel", e->sel, E / 50 + 2 * nb + 8}, {"hlen", e->hlen, nb * 6 * BZ_MAX_ALPHA}, {"ngroups", e->ngroups, nb * 4},
       {"prebits", e->prebits, nb * 4},
    };

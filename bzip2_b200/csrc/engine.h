@@ -8,8 +8,7 @@
 //   enc   u8 [E]    RLE1 output of the whole window; block b is enc[X[b], X[b+1])
 //   cend  u8 [E]    1 where an RLE1 chunk ends (block boundaries may only fall there)
 //   sa    u32[E]    per block: rotation start indices in sorted order (block-local)
-//   rank  u32[E]    per block: group-start rank of each rotation (block-local)
-//   nrank u32[E]    new ranks by sorted position (applied after each refinement round)
+//   rank  u64[E]    per block: group-start rank of each rotation, two generations per word
 //   keyA/keyB/idxB  u32[E] scratch for the large-segment radix path
 //   bwt   u8 [E]    last column;   z u8[E]  MTF positions;   mtfv u16[E + 2*nb]
 //   hist  u32[nb*hist_stride]  k-gram bucket histogram / cursors
@@ -84,7 +83,8 @@ struct Engine {
 
    // window buffers
    u8  *enc, *cend;
-   u32 *sa, *rank, *nrank, *keyA, *keyB, *idxB;
+   u32 *sa, *keyA, *keyB, *idxB;
+   u64 *rank;              // [E] tagged rank words (two generations per word)
    u8  *bwt, *z;
    u16 *mtfv;
    u32 *hist;

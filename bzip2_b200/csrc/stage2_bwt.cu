@@ -42,7 +42,8 @@ struct S2Params {
    const u32* X;
    u32 nb;
    u32 b0;                  // first block of the sub-batch being sorted
-   u32* sa; u32* rank; u32* nrank;
+   u32* sa;
+   u64* rank;               // tagged rank words, see rk_pack()
    u32* keyA; u32* keyB; u32* idxB;
    u32* hist;
    u32 hist_stride;         // bins reserved per block
@@ -61,6 +62,12 @@ __device__ __forceinline__ int seg_class(u32 len)
    if (len > MED_MAX) return CLS_LARGE;
    return CLS_C512 + (23 - __clz(len - 1));     // 257..512 -> +0, ..1024 -> +1, ..2048 -> +2, ..4096 -> +3
 }
+
+// Rank words carry two generations so that a refinement round can update ranks in place while
+// other CTAs still need the values the round started with: [tag:16 | old:24 | new:24].  A word
+// written in the current round (tag == round tag) is read through `old`, any other through `new`.
+__device__ __forceinline__ u64 rk_pack(u32 tag, u32 oldv, u32 newv) { return ((u64)tag << 48) | ((u64)oldv << 24) | (u64)newv; }
+__device__ __forceinline__ u32 rk_read(u64 w, u32 tag) { return ((u32)(w >> 48) == tag) ? ((u32)(w >> 24) & 0xffffffu) : ((u32)w & 0xffffffu); }
 
 // All 32 lanes of the warp must call this together.
 __device__ __forceinline__ void push_seg(const ListsDev& L, bool valid, u32 pos, u32 blk, u32 len)
@@ -181,7 +188,7 @@ __global__ void __launch_bounds__(KG_THREADS) k_kgram(S2Params p)
          u32 key = 0;
          for (u32 j = 0; j < k; j++) key = key * base + sc[s + j];
          if (MODE == KG_HIST) atomicAdd(&hist[key], 1u);
-         else if (MODE == KG_RANK) p.rank[xb + i] = hist[key];
+         else if (MODE == KG_RANK) p.rank[xb + i] = rk_pack(0xffffu, 0, hist[key]);
          else { const u32 pos = atomicAdd(&hist[key], 1u); p.sa[xb + pos] = i; }
       }
    }
@@ -255,7 +262,7 @@ __global__ void __launch_bounds__(256) k_refine_small(S2Params p, ListsDev Lout,
    if (active) {
       idx = p.sa[pos + sub];
       u32 t = idx + h; if (t >= n) t -= n;
-      key = p.rank[xb + t];
+      key = rk_read(p.rank[xb + t], round + 1);
    }
 #pragma unroll
    for (int k = 2; k <= LANES; k <<= 1) {
@@ -281,28 +288,12 @@ __global__ void __launch_bounds__(256) k_refine_small(S2Params p, ListsDev Lout,
    const u32 size = sub - gstart + 1;
    if (active) {
       p.sa[pos + sub] = idx;
-      p.nrank[pos + sub] = (pos - xb) + gstart;
+      p.rank[xb + idx] = rk_pack(round + 1, pos - xb, (pos - xb) + gstart);
    }
    const bool multi = is_end && size >= 2;
    const bool deep = (2u * h >= n);
    if (multi && deep) atomicMax(&p.power_q[b], size);
    push_seg(Lout, multi && !deep, pos + gstart, b, size);
-}
-
-template <int LANES>
-__global__ void __launch_bounds__(256) k_apply_small(S2Params p, const u32* items, u32 count)
-{
-   const u32 gid = blockIdx.x * blockDim.x + threadIdx.x;
-   const u32 seg = gid / LANES;
-   const u32 sub = gid % LANES;
-   if (seg >= count) return;
-   const u32 entry = items[seg];
-   const u32 pos = entry & 0x7ffffffu;
-   const u32 len = (entry >> 27) + 1;
-   if (sub >= len) return;
-   const u32 b = block_of(p, pos);
-   const u32 xb = p.X[b];
-   p.rank[xb + p.sa[pos + sub]] = p.nrank[pos + sub];
 }
 
 // ---- 2b. medium segments: bitonic sort of packed (key, local index) words ----------------
@@ -389,7 +380,7 @@ k_refine_medium(S2Params p, ListsDev Lout, const u64* items, u32 count, u32 roun
          const u32 idx = p.sa[pos + i];
          if (!WARP) sidx[i] = idx;
          u32 tt = idx + h; if (tt >= n) tt -= n;
-         w = (p.rank[xb + tt] << LBITS) | i;
+         w = (rk_read(p.rank[xb + tt], round + 1) << LBITS) | i;
       }
       v[r] = w;
    }
@@ -449,7 +440,7 @@ k_refine_medium(S2Params p, ListsDev Lout, const u64* items, u32 count, u32 roun
       bool is_end = false;
       if (in) {
          p.sa[pos + e] = idxs[r];
-         p.nrank[pos + e] = (pos - xb) + g;
+         p.rank[xb + idxs[r]] = rk_pack(round + 1, pos - xb, (pos - xb) + g);
          const u32 nx = (r == MS_ITEMS - 1) ? nextfirst : v[r + 1];
          is_end = (e == len - 1) || ((nx >> LBITS) != (v[r] >> LBITS));
       }
@@ -487,7 +478,7 @@ __global__ void __launch_bounds__(LG_THREADS) k_refine_large(S2Params p, ListsDe
    for (u32 i = threadIdx.x; i < len; i += LG_THREADS) {
       const u32 idx = p.sa[pos + i];
       u32 t = idx + h; if (t >= n) t -= n;
-      const u32 key = p.rank[xb + t];
+      const u32 key = rk_read(p.rank[xb + t], round + 1);
       p.keyA[pos + i] = key;
       atomicAdd(&binbase[0][key & 255], 1u);
       atomicAdd(&binbase[1][(key >> 8) & 255], 1u);
@@ -591,8 +582,9 @@ __global__ void __launch_bounds__(LG_THREADS) k_refine_large(S2Params p, ListsDe
          g = g ? g - 1 : 0;
          bool is_end = false;
          if (in) {
-            if (npass & 1) p.sa[pos + i] = ifin[pos + i];
-            p.nrank[pos + i] = (pos - xb) + g;
+            const u32 idx = ifin[pos + i];
+            if (npass & 1) p.sa[pos + i] = idx;
+            p.rank[xb + idx] = rk_pack(round + 1, pos - xb, (pos - xb) + g);
             is_end = (i == len - 1) || (kk[k + 2] != kk[k + 1]);
          }
          const u32 size = i - g + 1;
@@ -606,29 +598,6 @@ __global__ void __launch_bounds__(LG_THREADS) k_refine_large(S2Params p, ListsDe
    }
 }
 
-// one warp per segment (33..256 elements)
-__global__ void __launch_bounds__(256) k_apply_warp(S2Params p, const u64* items, u32 count)
-{
-   const u32 seg = blockIdx.x * 8 + (threadIdx.x >> 5);
-   if (seg >= count) return;
-   const u64 entry = items[seg];
-   const u32 pos = (u32)(entry >> 32);
-   const u32 b = (u32)(entry >> 20) & 0xfffu;
-   const u32 len = (u32)entry & 0xfffffu;
-   const u32 xb = p.X[b];
-   for (u32 i = lane_id(); i < len; i += 32) p.rank[xb + p.sa[pos + i]] = p.nrank[pos + i];
-}
-
-__global__ void __launch_bounds__(256) k_apply_big(S2Params p, const u64* items)
-{
-   const u64 entry = items[blockIdx.x];
-   const u32 pos = (u32)(entry >> 32);
-   const u32 b = (u32)(entry >> 20) & 0xfffu;
-   const u32 len = (u32)entry & 0xfffffu;
-   const u32 xb = p.X[b];
-   for (u32 i = threadIdx.x; i < len; i += blockDim.x) p.rank[xb + p.sa[pos + i]] = p.nrank[pos + i];
-}
-
 // ---- 3. last column -------------------------------------------------------------------
 __global__ void __launch_bounds__(KG_THREADS) k_bwt_out(S2Params p, u8* bwt, u32* origptr)
 {
@@ -638,7 +607,7 @@ __global__ void __launch_bounds__(KG_THREADS) k_bwt_out(S2Params p, u8* bwt, u32
    if (t0 >= n) return;
    const u8* T = p.T + xb;
    // rank of rotation 0: its final position, or the start of its tie group for exact powers
-   if (blockIdx.x == 0 && threadIdx.x == 0) origptr[b] = p.rank[xb];
+   if (blockIdx.x == 0 && threadIdx.x == 0) origptr[b] = (u32)p.rank[xb] & 0xffffffu;
 #pragma unroll 4
    for (int k = 0; k < KG_ITEMS; k++) {
       const u32 i = t0 + k * KG_THREADS + threadIdx.x;
@@ -667,20 +636,12 @@ static void launch_small(Engine* e, const S2Params& p, const ListsDev& Lout, con
    const u32 grid = (u32)((threads + 255) / 256);
    k_refine_small<LANES><<<grid, 256, 0, e->stream>>>(p, Lout, items, count, round);
 }
-template <int LANES>
-static void launch_apply_small(Engine* e, const S2Params& p, const u32* items, u32 count)
-{
-   const u64 threads = (u64)count * LANES;
-   const u32 grid = (u32)((threads + 255) / 256);
-   k_apply_small<LANES><<<grid, 256, 0, e->stream>>>(p, items, count);
-}
-
 int stage2_run(Engine* e, u32 nb, u32 E)
 {
    cudaStream_t st = e->stream;
    S2Params p;
    p.T = e->enc; p.X = e->bt.X; p.nb = nb;
-   p.sa = e->sa; p.rank = e->rank; p.nrank = e->nrank;
+   p.sa = e->sa; p.rank = e->rank;
    p.keyA = e->keyA; p.keyB = e->keyB; p.idxB = e->idxB;
    p.hist = e->hist; p.hist_stride = e->hist_stride; p.code = e->code; p.kk = e->kk; p.nbins = e->nbins;
    p.blockmap = e->blockmap;
@@ -738,19 +699,6 @@ int stage2_run(Engine* e, u32 nb, u32 E)
          for (int c = 0; c < N_CLASSES; c++) nl += cnt[c] ? 1u : 0u;
          e->launches += nl - 1;
          e->bwt_rounds++;
-         BZ_KCHECK(e);
-         if (cnt[CLS_LARGE]) k_apply_big<<<cnt[CLS_LARGE], 256, 0, st>>>(p, bi[5]);
-         if (cnt[CLS_C4K])   k_apply_big<<<cnt[CLS_C4K], 256, 0, st>>>(p, bi[4]);
-         if (cnt[CLS_C2K])   k_apply_big<<<cnt[CLS_C2K], 256, 0, st>>>(p, bi[3]);
-         if (cnt[CLS_C1K])   k_apply_big<<<cnt[CLS_C1K], 128, 0, st>>>(p, bi[2]);
-         if (cnt[CLS_C512])  k_apply_big<<<cnt[CLS_C512], 64, 0, st>>>(p, bi[1]);
-         if (cnt[CLS_W256])  k_apply_warp<<<(cnt[CLS_W256] + 7) / 8, 256, 0, st>>>(p, bi[0], cnt[CLS_W256]);
-         if (cnt[4]) launch_apply_small<32>(e, p, si[4], cnt[4]);
-         if (cnt[3]) launch_apply_small<16>(e, p, si[3], cnt[3]);
-         if (cnt[2]) launch_apply_small<8>(e, p, si[2], cnt[2]);
-         if (cnt[1]) launch_apply_small<4>(e, p, si[1], cnt[1]);
-         if (cnt[0]) launch_apply_small<2>(e, p, si[0], cnt[0]);
-         e->launches += nl - 1;
          BZ_KCHECK(e);
          cur = nxt;
       }
