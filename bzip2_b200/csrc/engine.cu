@@ -61,7 +61,7 @@ static void engine_free(EngineFull* e)
    if (!e) return;
    cudaSetDevice(e->device);
    void* dev[] = { e->enc, e->cend, e->sa, e->rank, e->keyA, e->keyB, e->idxB, e->bwt, e->z, e->mtfv, e->hist,
-                   e->blockmap, e->code, e->kk, e->nbins, e->tile_len, e->tile_ext, e->tile_carry, e->tile_size, e->tile_base, e->s1_scalars,
+                   e->blockmap, e->code, e->kk, e->nbins, e->hh, e->kbits, e->ksym, e->K, e->kscrA, e->kscrB, e->tile_len, e->tile_ext, e->tile_carry, e->tile_size, e->tile_base, e->s1_scalars,
                    e->mtf_summary, e->mtf_tilemeta, e->mtf_tilecnt, e->sel, e->hlen, e->hfreq, e->hcode, e->grpbits,
                    e->pre, e->prebits, e->ngroups, e->d_in, e->d_out,
                    e->bt.X, e->bt.P, e->bt.crc, e->bt.origptr, e->bt.power_q, e->bt.inuse, e->bt.ninuse, e->bt.nmtf,
@@ -101,6 +101,8 @@ static int engine_new(EngineFull** out, int device, int level, size_t window_byt
    {
       const char* g = getenv("BZ2_B200_S2_GROUP");
       e->s2_group = g ? (u32)atoi(g) : 0;
+      const char* tf = getenv("BZ2_B200_TEXT_FIRST");
+      e->text_first = tf ? (u32)atoi(tf) : 1;
    }
    if (window_bytes == 0) window_bytes = (size_t)96 << 20;
    // a window must be able to hold the input of one full block of pure runs (255 -> 5 bytes)
@@ -126,7 +128,8 @@ static int engine_new(EngineFull** out, int device, int level, size_t window_byt
       e->hist_stride = 1u << 16;
       while (e->hist_stride < (1u << 18) && e->hist_stride < e->nmax / 4) e->hist_stride <<= 1;
       ALLOC(e->hist, B * e->hist_stride);
-      ALLOC(e->code, B * 256); ALLOC(e->kk, B); ALLOC(e->nbins, B);
+      ALLOC(e->code, B * 256); ALLOC(e->kk, B); ALLOC(e->nbins, B); ALLOC(e->hh, B); ALLOC(e->kbits, B); ALLOC(e->ksym, B);
+      ALLOC(e->K, E + 64); ALLOC(e->kscrA, E + 64); ALLOC(e->kscrB, E + 64);
       ALLOC(e->blockmap, E / 4096 + 4);
       ALLOC(e->tile_len, ntiles); ALLOC(e->tile_ext, ntiles); ALLOC(e->tile_carry, ntiles);
       ALLOC(e->tile_size, ntiles); ALLOC(e->tile_base, ntiles);

@@ -91,7 +91,9 @@ struct Engine {
    u32 s2_group;           // blocks sorted per BWT sub-batch (0 = whole window)
    u32 hist_stride;        // k-gram bins reserved per block (power of two, 2^16..2^18)
    u8  *code;              // [blk_cap*256]
-   u32 *kk, *nbins;        // [blk_cap]
+   u32 *kk, *nbins, *hh, *kbits, *ksym;   // [blk_cap]
+   u64 *K, *kscrA, *kscrB; // [E] packed text keys; 64-bit key scratch of the large path
+   u32 text_first;         // first refinement round sorts by text keys (default on)
    u32 *blockmap;          // [enc_cap/4096 + 2] block id of each 4 KiB chunk of enc
    SegLists lists;
    BlockTables bt;

@@ -25,6 +25,7 @@
 // A segment that survives to depth >= n holds equal rotations: the block is an exact
 // power u^q; q is recorded in power_q[b] (the BWT bytes do not depend on their order).
 #include "engine.h"
+#include <stdlib.h>
 
 namespace bz {
 
@@ -49,6 +50,13 @@ struct S2Params {
    u32 hist_stride;         // bins reserved per block
    u8* code;                // [nb*256] dense symbol codes
    u32* kk;                 // [nb] k of the k-gram bucket sort = initial sorted depth
+   u32* hh;                 // [nb] k + m: depth after the text-key round
+   u32* kbits;              // [nb] m * bits-per-symbol: significant bits of a text key
+   u32* ksym;               // [nb] m | bits-per-symbol << 8
+   u64* K;                  // [E] packed codes of the next m symbols of every position
+   u64* kscrA; u64* kscrB;  // [E] 64-bit key scratch of the large-segment path
+   u32 text_first;          // round 0 sorts by text keys
+   u32 debug;
    u32* nbins;              // [nb] ninuse^k
    const u32* blockmap;
    u32* power_q;
@@ -156,13 +164,20 @@ __global__ void __launch_bounds__(256) k_codemap(S2Params p)
       while (tot > 1 && k < KG_MAXK && (u64)bins * tot <= (u64)p.hist_stride) { bins *= tot; k++; }
       p.kk[b] = k;
       p.nbins[b] = bins;
+      u32 bits = 1;
+      while ((1u << bits) < tot) bits++;
+      u32 m = 52u / bits;
+      if (m > 48u) m = 48u;
+      p.hh[b] = k + m;
+      p.kbits[b] = m * bits;
+      p.ksym[b] = m | (bits << 8);
    }
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(KG_THREADS) k_kgram(S2Params p)
 {
-   __shared__ u8 sc[KG_TILE + KG_MAXK + 8];
+   __shared__ u8 sc[KG_TILE + 64];
    __shared__ u8 cmap[256];
    const u32 b = p.b0 + blockIdx.y;
    const u32 xb = p.X[b], n = p.X[b + 1] - xb;
@@ -173,7 +188,9 @@ __global__ void __launch_bounds__(KG_THREADS) k_kgram(S2Params p)
    u32* hist = p.hist + (size_t)(b - p.b0) * p.hist_stride;
    cmap[threadIdx.x] = p.code[(size_t)b * 256 + threadIdx.x];
    __syncthreads();
-   const u32 span = min((u32)KG_TILE, n - t0) + k - 1;
+   const u32 msym = p.ksym[b] & 255u, mbits = p.ksym[b] >> 8;
+   const u32 halo = (MODE == KG_RANK && p.text_first) ? max(k, msym) : k;
+   const u32 span = min((u32)KG_TILE, n - t0) + halo - 1;
    for (u32 s = threadIdx.x; s < span; s += KG_THREADS) {
       u32 gi = t0 + s;
       if (gi >= n) gi = (gi - n < n) ? gi - n : gi % n;
@@ -188,7 +205,14 @@ __global__ void __launch_bounds__(KG_THREADS) k_kgram(S2Params p)
          u32 key = 0;
          for (u32 j = 0; j < k; j++) key = key * base + sc[s + j];
          if (MODE == KG_HIST) atomicAdd(&hist[key], 1u);
-         else if (MODE == KG_RANK) p.rank[xb + i] = rk_pack(0xffffu, 0, hist[key]);
+         else if (MODE == KG_RANK) {
+            p.rank[xb + i] = rk_pack(0xffffu, 0, hist[key]);
+            if (p.text_first) {
+               u64 kw = 0;
+               for (u32 j = 0; j < msym; j++) kw = (kw << mbits) | (u64)sc[s + j];
+               p.K[xb + i] = kw;
+            }
+         }
          else { const u32 pos = atomicAdd(&hist[key], 1u); p.sa[xb + pos] = i; }
       }
    }
@@ -244,10 +268,36 @@ __global__ void __launch_bounds__(256) k_seg_init(S2Params p, ListsDev L)
    push_seg(L, multi && !deep, xb + start, b, len);
 }
 
-// ---- 2a. small segments: sub-warp bitonic network ------------------------------------
-template <int LANES>
+// ---- 2. refinement rounds --------------------------------------------------------------
+// Round 0 (TEXT) sorts every k-gram bucket by the next m symbols taken from the packed text
+// keys K[] (depth k -> k+m).  Later rounds sort by the rank of the rotation `shift` further on
+// (classic doubling; depth d -> 2d).  Per block: kk = k, hh = k+m.
+template <bool TEXT> struct KeyOf { typedef u32 type; };
+template <> struct KeyOf<true> { typedef u64 type; };
+
+__device__ __forceinline__ u32 round_shift(const S2Params& p, u32 b, u32 round, u32* depth_after)
+{
+   const u32 k = p.kk[b];
+   if (!p.text_first) { const u32 sft = k << round; *depth_after = 2u * sft; return sft; }
+   if (round == 0) { *depth_after = p.hh[b]; return k; }
+   const u32 sft = p.hh[b] << (round - 1);
+   *depth_after = 2u * sft;
+   return sft;
+}
+
+template <bool TEXT>
+__device__ __forceinline__ typename KeyOf<TEXT>::type load_key(const S2Params& p, u32 xb, u32 n, u32 idx, u32 shift, u32 tag)
+{
+   u32 t = idx + shift; if (t >= n) t -= n;
+   if (TEXT) return (typename KeyOf<TEXT>::type)p.K[xb + t];
+   return (typename KeyOf<TEXT>::type)rk_read(p.rank[xb + t], tag);
+}
+
+// ---- 2a. small segments: sub-warp bitonic network, one element per lane --------------------
+template <int LANES, bool TEXT>
 __global__ void __launch_bounds__(256) k_refine_small(S2Params p, ListsDev Lout, const u32* items, u32 count, u32 round)
 {
+   typedef typename KeyOf<TEXT>::type KT;
    const u32 gid = blockIdx.x * blockDim.x + threadIdx.x;
    const u32 seg = gid / LANES;
    const u32 sub = gid % LANES;
@@ -255,20 +305,20 @@ __global__ void __launch_bounds__(256) k_refine_small(S2Params p, ListsDev Lout,
    const u32 entry = vseg ? items[seg] : 0;
    const u32 pos = entry & 0x7ffffffu;
    const u32 len = (entry >> 27) + 1;
-   u32 b = 0, xb = 0, n = 1, h = 0;
-   if (vseg) { b = block_of(p, pos); xb = p.X[b]; n = p.X[b + 1] - xb; h = p.kk[b] << round; }
+   u32 b = 0, xb = 0, n = 1, shift = 0, depth = 0;
+   if (vseg) { b = block_of(p, pos); xb = p.X[b]; n = p.X[b + 1] - xb; shift = round_shift(p, b, round, &depth); }
    const bool active = vseg && sub < len;
-   u32 idx = 0, key = 0xffffffffu;
+   u32 idx = 0;
+   KT key = ~(KT)0;
    if (active) {
       idx = p.sa[pos + sub];
-      u32 t = idx + h; if (t >= n) t -= n;
-      key = rk_read(p.rank[xb + t], round + 1);
+      key = load_key<TEXT>(p, xb, n, idx, shift, round + 1);
    }
 #pragma unroll
    for (int k = 2; k <= LANES; k <<= 1) {
 #pragma unroll
       for (int j = k >> 1; j > 0; j >>= 1) {
-         const u32 ok = __shfl_xor_sync(FULL, key, j);
+         const KT ok = __shfl_xor_sync(FULL, key, j);
          const u32 oi = __shfl_xor_sync(FULL, idx, j);
          const bool asc = ((sub & k) == 0);
          const bool low = ((sub & j) == 0);
@@ -276,8 +326,8 @@ __global__ void __launch_bounds__(256) k_refine_small(S2Params p, ListsDev Lout,
          if (take) { key = ok; idx = oi; }
       }
    }
-   const u32 pk = __shfl_up_sync(FULL, key, 1);
-   const u32 nk = __shfl_down_sync(FULL, key, 1);
+   const KT pk = __shfl_up_sync(FULL, key, 1);
+   const KT nk = __shfl_down_sync(FULL, key, 1);
    const bool head = active && (sub == 0 || pk != key);
    const u32 bal = __ballot_sync(FULL, head);
    const u32 sh = lane_id() & ~(u32)(LANES - 1);
@@ -291,7 +341,7 @@ __global__ void __launch_bounds__(256) k_refine_small(S2Params p, ListsDev Lout,
       p.rank[xb + idx] = rk_pack(round + 1, pos - xb, (pos - xb) + gstart);
    }
    const bool multi = is_end && size >= 2;
-   const bool deep = (2u * h >= n);
+   const bool deep = (depth >= n);
    if (multi && deep) atomicMax(&p.power_q[b], size);
    push_seg(Lout, multi && !deep, pos + gstart, b, size);
 }
@@ -302,9 +352,10 @@ __global__ void __launch_bounds__(256) k_refine_small(S2Params p, ListsDev Lout,
 // only distances >= 256 (other warps) go through shared memory.  The packed word makes a
 // compare-exchange a min/max pair.
 constexpr int MS_ITEMS = 8;
+constexpr int MS_LBITS = 12;              // local index bits packed under the key
 
-template <int THREADS>
-__device__ __forceinline__ void bitonic_blocked(u32 (&v)[MS_ITEMS], const u32 t, const u32 n2, u32* xch)
+template <int THREADS, typename VT>
+__device__ __forceinline__ void bitonic_blocked(VT (&v)[MS_ITEMS], const u32 t, const u32 n2, VT* xch)
 {
 #pragma unroll
    for (int k = 2; k <= THREADS * MS_ITEMS; k <<= 1) {
@@ -316,20 +367,20 @@ __device__ __forceinline__ void bitonic_blocked(u32 (&v)[MS_ITEMS], const u32 t,
             const u32 tj = (u32)j / MS_ITEMS;
             const bool keep_min = ((((t * MS_ITEMS) & (u32)k) == 0) == ((t & tj) == 0));
             __syncthreads();
-            reinterpret_cast<uint4*>(xch)[t * 2] = make_uint4(v[0], v[1], v[2], v[3]);
-            reinterpret_cast<uint4*>(xch)[t * 2 + 1] = make_uint4(v[4], v[5], v[6], v[7]);
-            __syncthreads();
-            const uint4 a = reinterpret_cast<const uint4*>(xch)[(t ^ tj) * 2];
-            const uint4 c = reinterpret_cast<const uint4*>(xch)[(t ^ tj) * 2 + 1];
-            const u32 o[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
 #pragma unroll
-            for (int r = 0; r < MS_ITEMS; r++) v[r] = keep_min ? min(v[r], o[r]) : max(v[r], o[r]);
+            for (int r = 0; r < MS_ITEMS; r++) xch[t * MS_ITEMS + r] = v[r];
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < MS_ITEMS; r++) {
+               const VT o = xch[(t ^ tj) * MS_ITEMS + r];
+               v[r] = keep_min ? min(v[r], o) : max(v[r], o);
+            }
          } else if (j >= MS_ITEMS) {
             const u32 lj = (u32)j / MS_ITEMS;
             const bool keep_min = ((((t * MS_ITEMS) & (u32)k) == 0) == ((t & lj) == 0));
 #pragma unroll
             for (int r = 0; r < MS_ITEMS; r++) {
-               const u32 o = __shfl_xor_sync(FULL, v[r], lj);
+               const VT o = __shfl_xor_sync(FULL, v[r], lj);
                v[r] = keep_min ? min(v[r], o) : max(v[r], o);
             }
          } else {
@@ -337,7 +388,7 @@ __device__ __forceinline__ void bitonic_blocked(u32 (&v)[MS_ITEMS], const u32 t,
             for (int r = 0; r < MS_ITEMS; r++) {
                if ((r & j) == 0) {
                   const bool asc = (((t * MS_ITEMS + r) & (u32)k) == 0);
-                  const u32 lo = min(v[r], v[r | j]), hi = max(v[r], v[r | j]);
+                  const VT lo = min(v[r], v[r | j]), hi = max(v[r], v[r | j]);
                   v[r] = asc ? lo : hi;
                   v[r | j] = asc ? hi : lo;
                }
@@ -348,15 +399,15 @@ __device__ __forceinline__ void bitonic_blocked(u32 (&v)[MS_ITEMS], const u32 t,
 }
 
 // One segment per group of THREADS threads (THREADS = 32: a warp, no shared memory;
-// THREADS = 512: a CTA).  LBITS = bits of the local index packed under the key.
-template <int THREADS, int LBITS>
+// THREADS >= 64: a CTA).
+template <int THREADS, bool TEXT>
 __global__ void __launch_bounds__(THREADS == 32 ? 256 : THREADS)
 k_refine_medium(S2Params p, ListsDev Lout, const u64* items, u32 count, u32 round)
 {
+   typedef typename KeyOf<TEXT>::type VT;            // packed word: key << 12 | local
    constexpr int CAP = THREADS * MS_ITEMS;
    constexpr bool WARP = (THREADS == 32);
-   __shared__ u32 xch[WARP ? 1 : CAP];
-   __shared__ u32 sidx[WARP ? 1 : CAP];
+   __shared__ __align__(16) VT xch[WARP ? 2 : CAP];
    __shared__ u32 ssm[34];
    const u32 t = WARP ? lane_id() : threadIdx.x;
    const u32 seg = WARP ? (blockIdx.x * 8 + (threadIdx.x >> 5)) : blockIdx.x;
@@ -365,40 +416,39 @@ k_refine_medium(S2Params p, ListsDev Lout, const u64* items, u32 count, u32 roun
    const u32 pos = (u32)(entry >> 32);
    const u32 b = (u32)(entry >> 20) & 0xfffu;
    const u32 len = (u32)entry & 0xfffffu;
-   u32 xb = 0, n = 1, h = 0;
-   if (vseg) { xb = p.X[b]; n = p.X[b + 1] - xb; h = p.kk[b] << round; }
+   u32 xb = 0, n = 1, shift = 0, depth = 0;
+   if (vseg) { xb = p.X[b]; n = p.X[b + 1] - xb; shift = round_shift(p, b, round, &depth); }
    u32 n2 = 64;
    while (n2 < len) n2 <<= 1;
    // blocked load: thread t owns sequence positions t*8 .. t*8+7; the element's local id travels
-   // in the low bits of the packed word.  Padding (0xffffffff) sorts to the end of [0, n2).
-   u32 v[MS_ITEMS];
+   // in the low bits of the packed word.  Padding (all ones) sorts to the end of [0, n2).
+   VT v[MS_ITEMS];
 #pragma unroll
    for (int r = 0; r < MS_ITEMS; r++) {
       const u32 i = t * MS_ITEMS + (u32)r;
-      u32 w = 0xffffffffu;
+      VT w = ~(VT)0;
       if (i < len) {
          const u32 idx = p.sa[pos + i];
-         if (!WARP) sidx[i] = idx;
-         u32 tt = idx + h; if (tt >= n) tt -= n;
-         w = (rk_read(p.rank[xb + tt], round + 1) << LBITS) | i;
+         w = (load_key<TEXT>(p, xb, n, idx, shift, round + 1) << MS_LBITS) | (VT)i;
       }
       v[r] = w;
    }
-   bitonic_blocked<THREADS>(v, t, n2, xch);
+   bitonic_blocked<THREADS, VT>(v, t, n2, xch);
    // sorted position e = t*8 + r.  Heads, group starts (1-based running max), ends.
-   u32 prevlast = __shfl_up_sync(FULL, v[MS_ITEMS - 1], 1);
+   VT prevlast = __shfl_up_sync(FULL, v[MS_ITEMS - 1], 1);
+   VT nextfirst = __shfl_down_sync(FULL, v[0], 1);
    if (!WARP) {
+      // indices are clamped so that a speculated shared-memory load can never leave the array
+      const u32 wi = threadIdx.x >> 5;
+      const u32 pi = wi ? wi - 1 : 0;
+      const u32 ni = (wi + 1 < (u32)(THREADS / 32)) ? wi + 1 : wi;
       __syncthreads();
-      if (lane_id() == 31) xch[threadIdx.x >> 5] = v[MS_ITEMS - 1];
+      if (lane_id() == 31) xch[wi] = v[MS_ITEMS - 1];
+      if (lane_id() == 0) xch[32 + wi] = v[0];
       __syncthreads();
-      if (lane_id() == 0 && t > 0) prevlast = xch[(threadIdx.x >> 5) - 1];
-   }
-   u32 nextfirst = __shfl_down_sync(FULL, v[0], 1);
-   if (!WARP) {
-      __syncthreads();
-      if (lane_id() == 0) xch[threadIdx.x >> 5] = v[0];
-      __syncthreads();
-      if (lane_id() == 31 && (threadIdx.x >> 5) + 1 < THREADS / 32) nextfirst = xch[(threadIdx.x >> 5) + 1];
+      const VT pl = xch[pi], nf = xch[32 + ni];
+      if (lane_id() == 0 && wi > 0) prevlast = pl;
+      if (lane_id() == 31 && wi + 1 < (u32)(THREADS / 32)) nextfirst = nf;
    }
    const u32 base = t * MS_ITEMS;
    u32 last = 0, gs[MS_ITEMS];
@@ -406,8 +456,8 @@ k_refine_medium(S2Params p, ListsDev Lout, const u64* items, u32 count, u32 roun
    for (int r = 0; r < MS_ITEMS; r++) {
       const u32 e = base + r;
       if (e < len) {
-         const u32 pv = (r == 0) ? prevlast : v[r - 1];
-         if (e == 0 || (pv >> LBITS) != (v[r] >> LBITS)) last = e + 1;
+         const VT pv = (r == 0) ? prevlast : v[r - 1];
+         if (e == 0 || (pv >> MS_LBITS) != (v[r] >> MS_LBITS)) last = e + 1;
       }
       gs[r] = last;
    }
@@ -426,11 +476,11 @@ k_refine_medium(S2Params p, ListsDev Lout, const u64* items, u32 count, u32 roun
 #pragma unroll
    for (int r = 0; r < MS_ITEMS; r++) {
       const u32 e = base + r;
-      const u32 local = v[r] & ((1u << LBITS) - 1u);
-      idxs[r] = (e < len) ? (WARP ? p.sa[pos + local] : sidx[local]) : 0;
+      const u32 local = (u32)v[r] & ((1u << MS_LBITS) - 1u);
+      idxs[r] = (e < len) ? p.sa[pos + local] : 0;
    }
    if (WARP) __syncwarp(); else __syncthreads();
-   const bool deep = (2u * h >= n);
+   const bool deep = (depth >= n);
 #pragma unroll
    for (int r = 0; r < MS_ITEMS; r++) {
       const u32 e = base + r;
@@ -441,8 +491,8 @@ k_refine_medium(S2Params p, ListsDev Lout, const u64* items, u32 count, u32 roun
       if (in) {
          p.sa[pos + e] = idxs[r];
          p.rank[xb + idxs[r]] = rk_pack(round + 1, pos - xb, (pos - xb) + g);
-         const u32 nx = (r == MS_ITEMS - 1) ? nextfirst : v[r + 1];
-         is_end = (e == len - 1) || ((nx >> LBITS) != (v[r] >> LBITS));
+         const VT nx = (r == MS_ITEMS - 1) ? nextfirst : v[r + 1];
+         is_end = (e == len - 1) || ((nx >> MS_LBITS) != (v[r] >> MS_LBITS));
       }
       const u32 size = e - g + 1;
       const bool multi = in && is_end && size >= 2;
@@ -456,11 +506,14 @@ constexpr int LG_THREADS = 1024;
 constexpr int LG_ITEMS = 4;
 constexpr int LG_TILE = LG_THREADS * LG_ITEMS;
 constexpr int LG_WARPS = LG_THREADS / 32;
+constexpr int LG_MAXPASS = 7;
 
+template <bool TEXT>
 __global__ void __launch_bounds__(LG_THREADS) k_refine_large(S2Params p, ListsDev Lout, const u64* items, u32 round)
 {
+   typedef typename KeyOf<TEXT>::type KT;
    __shared__ u32 whist[LG_WARPS][256];
-   __shared__ u32 binbase[3][256];
+   __shared__ u32 binbase[TEXT ? LG_MAXPASS : 3][256];
    __shared__ u32 ssm[34];
    __shared__ u32 s_carry;
    const u64 entry = items[blockIdx.x];
@@ -468,24 +521,24 @@ __global__ void __launch_bounds__(LG_THREADS) k_refine_large(S2Params p, ListsDe
    const u32 b = (u32)(entry >> 20) & 0xfffu;
    const u32 len = (u32)entry & 0xfffffu;
    const u32 xb = p.X[b], n = p.X[b + 1] - xb;
-   const int npass = (n > 65536u) ? 3 : 2;
-   const u32 h = p.kk[b] << round;
+   u32 depth;
+   const u32 shift0 = round_shift(p, b, round, &depth);
+   const int npass = TEXT ? (int)((p.kbits[b] + 7) >> 3) : ((n > 65536u) ? 3 : 2);
+   KT* const kA = TEXT ? reinterpret_cast<KT*>(p.kscrA) : reinterpret_cast<KT*>(p.keyA);
+   KT* const kB = TEXT ? reinterpret_cast<KT*>(p.kscrB) : reinterpret_cast<KT*>(p.keyB);
    const u32 w = threadIdx.x >> 5, l = lane_id();
 
-   for (u32 i = threadIdx.x; i < 3 * 256; i += LG_THREADS) (&binbase[0][0])[i] = 0;
+   for (u32 i = threadIdx.x; i < (u32)npass * 256; i += LG_THREADS) (&binbase[0][0])[i] = 0;
    __syncthreads();
    // phase A: gather keys, digit histograms
    for (u32 i = threadIdx.x; i < len; i += LG_THREADS) {
       const u32 idx = p.sa[pos + i];
-      u32 t = idx + h; if (t >= n) t -= n;
-      const u32 key = rk_read(p.rank[xb + t], round + 1);
-      p.keyA[pos + i] = key;
-      atomicAdd(&binbase[0][key & 255], 1u);
-      atomicAdd(&binbase[1][(key >> 8) & 255], 1u);
-      if (npass == 3) atomicAdd(&binbase[2][(key >> 16) & 255], 1u);
+      const KT key = load_key<TEXT>(p, xb, n, idx, shift0, round + 1);
+      kA[pos + i] = key;
+      for (int q = 0; q < npass; q++) atomicAdd(&binbase[q][(u32)(key >> (8 * q)) & 255], 1u);
    }
    __syncthreads();
-   if (w < 3) {
+   if (w < (u32)npass) {
       // exclusive scan of 256 bins by one warp: 8 per lane
       u32 v[8], s = 0;
 #pragma unroll
@@ -498,23 +551,24 @@ __global__ void __launch_bounds__(LG_THREADS) k_refine_large(S2Params p, ListsDe
 
    // phase B: passes
    for (int pass = 0; pass < npass; pass++) {
-      const u32* ksrc = (pass & 1) ? p.keyB : p.keyA;
+      const KT* ksrc = (pass & 1) ? kB : kA;
       const u32* isrc = (pass & 1) ? p.idxB : p.sa;
-      u32* kdst = (pass & 1) ? p.keyA : p.keyB;
+      KT* kdst = (pass & 1) ? kA : kB;
       u32* idst = (pass & 1) ? p.sa : p.idxB;
       const int shift = pass * 8;
       for (u32 tb = 0; tb < len; tb += LG_TILE) {
 #pragma unroll
          for (int k = 0; k < 8; k++) whist[w][l * 8 + k] = 0;
          __syncwarp();
-         u32 key[LG_ITEMS], idx[LG_ITEMS], rk[LG_ITEMS];
+         KT key[LG_ITEMS];
+         u32 idx[LG_ITEMS], rk[LG_ITEMS];
 #pragma unroll
          for (int k = 0; k < LG_ITEMS; k++) {
             const u32 i = tb + w * (32 * LG_ITEMS) + k * 32 + l;
             const bool valid = i < len;
             key[k] = valid ? ksrc[pos + i] : 0;
             idx[k] = valid ? isrc[pos + i] : 0;
-            const u32 d = (key[k] >> shift) & 255;
+            const u32 d = (u32)(key[k] >> shift) & 255;
             const u32 m = __match_any_sync(FULL, valid ? d : 0x1000u);
             const u32 old = whist[w][d];
             __syncwarp();
@@ -538,7 +592,7 @@ __global__ void __launch_bounds__(LG_THREADS) k_refine_large(S2Params p, ListsDe
          for (int k = 0; k < LG_ITEMS; k++) {
             const u32 i = tb + w * (32 * LG_ITEMS) + k * 32 + l;
             if (i < len) {
-               const u32 d = (key[k] >> shift) & 255;
+               const u32 d = (u32)(key[k] >> shift) & 255;
                const u32 dst = whist[w][d] + rk[k];
                kdst[pos + dst] = key[k];
                idst[pos + dst] = idx[k];
@@ -549,18 +603,18 @@ __global__ void __launch_bounds__(LG_THREADS) k_refine_large(S2Params p, ListsDe
       __threadfence_block();
    }
    // phase C: group boundaries, new ranks, next-round segments
-   const u32* kfin = (npass & 1) ? p.keyB : p.keyA;
+   const KT* kfin = (npass & 1) ? kB : kA;
    const u32* ifin = (npass & 1) ? p.idxB : p.sa;
-   const bool deep = (2u * h >= n);
+   const bool deep = (depth >= n);
    if (threadIdx.x == 0) s_carry = 0;
    __syncthreads();
    for (u32 tb = 0; tb < len; tb += LG_TILE) {
       const u32 base = tb + threadIdx.x * LG_ITEMS;
-      u32 kk[LG_ITEMS + 2];
+      KT kk[LG_ITEMS + 2];
 #pragma unroll
       for (int k = 0; k < LG_ITEMS + 2; k++) {
          const i64 i = (i64)base + k - 1;
-         kk[k] = (i >= 0 && i < (i64)len) ? kfin[pos + (u32)i] : 0xffffffffu;
+         kk[k] = (i >= 0 && i < (i64)len) ? kfin[pos + (u32)i] : ~(KT)0;
       }
       u32 last = 0, gs[LG_ITEMS];
 #pragma unroll
@@ -629,13 +683,37 @@ static ListsDev lists_dev(Engine* e, int which)
    return L;
 }
 
+// BZ2_B200_DEBUG_SYNC=1: synchronise after every refinement launch and name the kernel that faulted
+static bool dbg_sync(Engine* e, const char* what)
+{
+   static int on = -1;
+   if (on < 0) { const char* v = getenv("BZ2_B200_DEBUG_SYNC"); on = (v && *v >= '1') ? 1 : 0; }
+   if (!on) return true;
+   cudaError_t c = cudaStreamSynchronize(e->stream);
+   if (c == cudaSuccess) c = cudaGetLastError();
+   if (c != cudaSuccess) { fprintf(stderr, "[bz2b200] %s: %s\n", what, cudaGetErrorString(c)); return false; }
+   return true;
+}
+
 template <int LANES>
-static void launch_small(Engine* e, const S2Params& p, const ListsDev& Lout, const u32* items, u32 count, u32 round)
+static void launch_small(Engine* e, const S2Params& p, const ListsDev& Lout, const u32* items, u32 count, u32 round, bool text)
 {
    const u64 threads = (u64)count * LANES;
    const u32 grid = (u32)((threads + 255) / 256);
-   k_refine_small<LANES><<<grid, 256, 0, e->stream>>>(p, Lout, items, count, round);
+   if (text) k_refine_small<LANES, true><<<grid, 256, 0, e->stream>>>(p, Lout, items, count, round);
+   else      k_refine_small<LANES, false><<<grid, 256, 0, e->stream>>>(p, Lout, items, count, round);
+   char nm[64]; snprintf(nm, sizeof nm, "k_refine_small<%d,%d> count=%u round=%u", LANES, (int)text, count, round); dbg_sync(e, nm);
 }
+template <int THREADS>
+static void launch_medium(Engine* e, const S2Params& p, const ListsDev& Lout, const u64* items, u32 count, u32 round, bool text)
+{
+   const u32 grid = (THREADS == 32) ? (count + 7) / 8 : count;
+   const u32 block = (THREADS == 32) ? 256 : THREADS;
+   if (text) k_refine_medium<THREADS, true><<<grid, block, 0, e->stream>>>(p, Lout, items, count, round);
+   else      k_refine_medium<THREADS, false><<<grid, block, 0, e->stream>>>(p, Lout, items, count, round);
+   char nm[64]; snprintf(nm, sizeof nm, "k_refine_medium<%d,%d> count=%u round=%u", THREADS, (int)text, count, round); dbg_sync(e, nm);
+}
+
 int stage2_run(Engine* e, u32 nb, u32 E)
 {
    cudaStream_t st = e->stream;
@@ -644,6 +722,9 @@ int stage2_run(Engine* e, u32 nb, u32 E)
    p.sa = e->sa; p.rank = e->rank;
    p.keyA = e->keyA; p.keyB = e->keyB; p.idxB = e->idxB;
    p.hist = e->hist; p.hist_stride = e->hist_stride; p.code = e->code; p.kk = e->kk; p.nbins = e->nbins;
+   p.hh = e->hh; p.kbits = e->kbits; p.ksym = e->ksym; p.K = e->K; p.kscrA = e->kscrA; p.kscrB = e->kscrB;
+   p.text_first = e->text_first;
+   p.debug = 0;
    p.blockmap = e->blockmap;
    p.power_q = e->bt.power_q; p.inuse = e->bt.inuse; p.ninuse = e->bt.ninuse;
 
@@ -668,6 +749,7 @@ int stage2_run(Engine* e, u32 nb, u32 E)
       k_kgram<KG_RANK><<<gtiles, KG_THREADS, 0, st>>>(p);                                       BZ_KCHECK(e);
       k_kgram<KG_SCATTER><<<gtiles, KG_THREADS, 0, st>>>(p);                                    BZ_KCHECK(e);
       k_seg_init<<<dim3((e->hist_stride + 255) / 256, g), 256, 0, st>>>(p, lists_dev(e, 0));    BZ_KCHECK(e);
+      dbg_sync(e, "k-gram phase");
 
       int cur = 0;
       for (u32 round = 0; ; round++) {
@@ -684,17 +766,22 @@ int stage2_run(Engine* e, u32 nb, u32 E)
          ListsDev Lout = lists_dev(e, nxt);
          u32** si = e->lists.small_items[cur];
          u64** bi = e->lists.big_items[cur];
-         if (cnt[CLS_LARGE]) k_refine_large<<<cnt[CLS_LARGE], LG_THREADS, 0, st>>>(p, Lout, bi[5], round);
-         if (cnt[CLS_C4K])   k_refine_medium<512, 12><<<cnt[CLS_C4K], 512, 0, st>>>(p, Lout, bi[4], cnt[CLS_C4K], round);
-         if (cnt[CLS_C2K])   k_refine_medium<256, 12><<<cnt[CLS_C2K], 256, 0, st>>>(p, Lout, bi[3], cnt[CLS_C2K], round);
-         if (cnt[CLS_C1K])   k_refine_medium<128, 12><<<cnt[CLS_C1K], 128, 0, st>>>(p, Lout, bi[2], cnt[CLS_C1K], round);
-         if (cnt[CLS_C512])  k_refine_medium<64, 12><<<cnt[CLS_C512], 64, 0, st>>>(p, Lout, bi[1], cnt[CLS_C512], round);
-         if (cnt[CLS_W256])  k_refine_medium<32, 8><<<(cnt[CLS_W256] + 7) / 8, 256, 0, st>>>(p, Lout, bi[0], cnt[CLS_W256], round);
-         if (cnt[4]) launch_small<32>(e, p, Lout, si[4], cnt[4], round);
-         if (cnt[3]) launch_small<16>(e, p, Lout, si[3], cnt[3], round);
-         if (cnt[2]) launch_small<8>(e, p, Lout, si[2], cnt[2], round);
-         if (cnt[1]) launch_small<4>(e, p, Lout, si[1], cnt[1], round);
-         if (cnt[0]) launch_small<2>(e, p, Lout, si[0], cnt[0], round);
+         const bool text = (round == 0) && e->text_first;
+         if (cnt[CLS_LARGE]) {
+            if (text) k_refine_large<true><<<cnt[CLS_LARGE], LG_THREADS, 0, st>>>(p, Lout, bi[5], round);
+            else      k_refine_large<false><<<cnt[CLS_LARGE], LG_THREADS, 0, st>>>(p, Lout, bi[5], round);
+            dbg_sync(e, "k_refine_large");
+         }
+         if (cnt[CLS_C4K])   launch_medium<512>(e, p, Lout, bi[4], cnt[CLS_C4K], round, text);
+         if (cnt[CLS_C2K])   launch_medium<256>(e, p, Lout, bi[3], cnt[CLS_C2K], round, text);
+         if (cnt[CLS_C1K])   launch_medium<128>(e, p, Lout, bi[2], cnt[CLS_C1K], round, text);
+         if (cnt[CLS_C512])  launch_medium<64>(e, p, Lout, bi[1], cnt[CLS_C512], round, text);
+         if (cnt[CLS_W256])  launch_medium<32>(e, p, Lout, bi[0], cnt[CLS_W256], round, text);
+         if (cnt[4]) launch_small<32>(e, p, Lout, si[4], cnt[4], round, text);
+         if (cnt[3]) launch_small<16>(e, p, Lout, si[3], cnt[3], round, text);
+         if (cnt[2]) launch_small<8>(e, p, Lout, si[2], cnt[2], round, text);
+         if (cnt[1]) launch_small<4>(e, p, Lout, si[1], cnt[1], round, text);
+         if (cnt[0]) launch_small<2>(e, p, Lout, si[0], cnt[0], round, text);
          u32 nl = 0;
          for (int c = 0; c < N_CLASSES; c++) nl += cnt[c] ? 1u : 0u;
          e->launches += nl - 1;
