@@ -46,6 +46,12 @@ struct EngineFull : Engine {
    bool debug_keep;
    u32 last_nb, last_E;
    cudaEvent_t ev[6];
+   // host path: double-buffered input so the next window's H2D overlaps this window's kernels
+   u8* d_in2;
+   cudaStream_t copy_stream;
+   cudaEvent_t ev_h2d[2];
+   void (*after_s1)(EngineFull*, u32 consumed, void* ctx);
+   void* after_s1_ctx;
 };
 
 template <typename T>
@@ -76,6 +82,9 @@ static void engine_free(EngineFull* e)
    if (e->h_blk) cudaFreeHost(e->h_blk);
    if (e->h_in) cudaFreeHost(e->h_in);
    if (e->h_out) cudaFreeHost(e->h_out);
+   if (e->d_in2) cudaFree(e->d_in2);
+   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+   for (int i = 0; i < 2; i++) if (e->ev_h2d[i]) cudaEventDestroy(e->ev_h2d[i]);
    for (int i = 0; i < 6; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
    if (e->own_stream) cudaStreamDestroy(e->own_stream);
    free(e);
@@ -175,6 +184,12 @@ static int ensure_staging(EngineFull* e, bool need_hin)
    if (!e->d_in)  { cudaError_t c = cudaMalloc(reinterpret_cast<void**>(&e->d_in), (size_t)e->win_cap + 64); if (c != cudaSuccess) return engine_fail(e, c, __FILE__, __LINE__); }
    if (!e->d_out) { cudaError_t c = cudaMalloc(reinterpret_cast<void**>(&e->d_out), e->out_cap); if (c != cudaSuccess) return engine_fail(e, c, __FILE__, __LINE__); }
    if (!e->h_out) { cudaError_t c = cudaMallocHost(reinterpret_cast<void**>(&e->h_out), e->out_cap); if (c != cudaSuccess) return engine_fail(e, c, __FILE__, __LINE__); }
+   if (!e->d_in2) { cudaError_t c = cudaMalloc(reinterpret_cast<void**>(&e->d_in2), (size_t)e->win_cap + 64); if (c != cudaSuccess) return engine_fail(e, c, __FILE__, __LINE__); }
+   if (!e->copy_stream) {
+      cudaError_t c = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking);
+      if (c != cudaSuccess) return engine_fail(e, c, __FILE__, __LINE__);
+      for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&e->ev_h2d[i], cudaEventDisableTiming);
+   }
    if (need_hin && !e->h_in) { cudaError_t c = cudaMallocHost(reinterpret_cast<void**>(&e->h_in), (size_t)e->win_cap); if (c != cudaSuccess) return engine_fail(e, c, __FILE__, __LINE__); }
    return 0;
 }
@@ -198,6 +213,7 @@ static int run_window(EngineFull* e, const u8* d_in, u32 W, bool is_final, bool 
    int rc = stage1_run(e, d_in, W, is_final, tail_merge, &nb, &cons, &E);
    if (rc) { snprintf(g_err, sizeof g_err, "%s", e->err); return rc; }
    cudaEventRecord(e->ev[1], st);
+   if (e->after_s1) e->after_s1(e, cons, e->after_s1_ctx);
    *consumed = cons; *nb_out = nb;
    e->last_nb = nb; e->last_E = E;
    if (nb == 0) return 0;
@@ -276,12 +292,32 @@ static int window_to_sink(EngineFull* e, const u8* d_in, u32 W, bool is_final, b
    const u64 end_bit = ss.bits;
    const size_t nbytes = (size_t)((end_bit - origin_bit + 7) >> 3);
    if (nbytes > e->out_cap) return set_err(BZ2B200_EINTERNAL, "window output exceeds staging capacity");
-   BZ_CUDA(e, cudaMemcpyAsync(e->h_out, e->d_out, nbytes, cudaMemcpyDeviceToHost, st));
-   BZ_CUDA(e, cudaStreamSynchronize(st));
    const size_t skip = (size_t)((bits_before >> 3) - (origin_bit >> 3));
    const size_t full_end = (size_t)((end_bit >> 3) - (origin_bit >> 3));     // first byte that is not complete
+   if (!sk.fn) {
+      // memory sink: copy straight into the caller's buffer, then patch the carried bits
+      const size_t nfull = full_end - skip;
+      if (sk.len + nfull > sk.cap) return BZ2B200_EOUTFULL;
+      if (nfull) BZ_CUDA(e, cudaMemcpyAsync(sk.dst + sk.len, e->d_out + skip, nfull, cudaMemcpyDeviceToHost, st));
+      BZ_CUDA(e, cudaMemcpyAsync(e->h_out, e->d_out + full_end, 1, cudaMemcpyDeviceToHost, st));
+      BZ_CUDA(e, cudaStreamSynchronize(st));
+      if (nfull) {
+         if (ss.ncarry) sk.dst[sk.len] |= ss.carry;
+         sk.len += nfull;
+         ss.ncarry = (u32)(end_bit & 7);
+         ss.carry = ss.ncarry ? e->h_out[0] : 0;
+      } else {
+         // the window ended inside the byte it started in
+         ss.carry = (u8)(ss.carry | e->h_out[0]);
+         ss.ncarry = (u32)(end_bit & 7);
+      }
+      return 0;
+   }
+   BZ_CUDA(e, cudaMemcpyAsync(e->h_out, e->d_out, nbytes, cudaMemcpyDeviceToHost, st));
+   BZ_CUDA(e, cudaStreamSynchronize(st));
    if (ss.ncarry) e->h_out[skip] |= ss.carry;
    if (full_end > skip) { rc = sk.put(e->h_out + skip, full_end - skip); if (rc) return rc; }
+   else { ss.carry = e->h_out[skip]; ss.ncarry = (u32)(end_bit & 7); return 0; }
    ss.ncarry = (u32)(end_bit & 7);
    ss.carry = ss.ncarry ? e->h_out[full_end] : 0;
    if (full_end == skip && (bits_before & 7)) { /* still inside the same partial byte */ }
@@ -363,17 +399,47 @@ int bz2b200_compress_host(bz2b200_engine* h, const void* src, size_t src_len, vo
    if ((rc = begin_stream(e, sk))) return rc;
    const u8* in = static_cast<const u8*>(src);
    const bool tail_merge = !(flags & BZ2B200_TAIL_STREAMED);
+   // Pinned (or registered) source: the next window's H2D is issued as soon as stage 1 has fixed
+   // where it starts, on a second stream, so it overlaps stages 2-4 of the current window.
+   bool pinned = false;
+   if (src_len) {
+      cudaPointerAttributes at;
+      if (cudaPointerGetAttributes(&at, src) == cudaSuccess) pinned = (at.type == cudaMemoryTypeHost);
+      else cudaGetLastError();
+   }
+   struct Prefetch { const u8* in; size_t n, pos; int buf; bool issued; u8* dbuf[2]; } pf;
+   pf.in = in; pf.n = src_len; pf.pos = 0; pf.buf = 0; pf.issued = false; pf.dbuf[0] = e->d_in; pf.dbuf[1] = e->d_in2;
+   e->after_s1 = nullptr; e->after_s1_ctx = &pf;
+   if (pinned) {
+      e->after_s1 = [](EngineFull* ee, u32 cons, void* ctx) {
+         Prefetch* p = static_cast<Prefetch*>(ctx);
+         const size_t next = p->pos + cons;
+         p->issued = false;
+         if (cons == 0 || next >= p->n) return;
+         const size_t W2 = (p->n - next < ee->win_cap) ? (p->n - next) : ee->win_cap;
+         const int nb = p->buf ^ 1;
+         if (cudaMemcpyAsync(p->dbuf[nb], p->in + next, W2, cudaMemcpyHostToDevice, ee->copy_stream) != cudaSuccess) { cudaGetLastError(); return; }
+         cudaEventRecord(ee->ev_h2d[nb], ee->copy_stream);
+         p->issued = true;
+      };
+   }
    size_t pos = 0;
    while (pos < src_len) {
       const size_t W = (src_len - pos < e->win_cap) ? (src_len - pos) : e->win_cap;
       const bool fin = (pos + W == src_len);
-      BZ_CUDA(e, cudaMemcpyAsync(e->d_in, in + pos, W, cudaMemcpyHostToDevice, e->stream));
+      pf.pos = pos;
+      u8* dcur = pf.dbuf[pf.buf];
+      if (pf.issued) BZ_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_h2d[pf.buf], 0));
+      else BZ_CUDA(e, cudaMemcpyAsync(dcur, in + pos, W, cudaMemcpyHostToDevice, e->stream));
+      pf.issued = false;
       u32 cons = 0;
-      rc = window_to_sink(e, e->d_in, (u32)W, fin, tail_merge, sk, &cons);
-      if (rc) return rc;
-      if (cons == 0) return set_err(BZ2B200_EINTERNAL, "window made no progress");
+      rc = window_to_sink(e, dcur, (u32)W, fin, tail_merge, sk, &cons);
+      if (rc) { e->after_s1 = nullptr; cudaStreamSynchronize(e->copy_stream); return rc; }
+      if (cons == 0) { e->after_s1 = nullptr; cudaStreamSynchronize(e->copy_stream); return set_err(BZ2B200_EINTERNAL, "window made no progress"); }
       pos += cons;
+      if (pf.issued) pf.buf ^= 1;
    }
+   e->after_s1 = nullptr;
    if ((rc = finish_stream(e, sk))) return rc;
    *dst_len = sk.len;
    e->ss.st.in_bytes = src_len; e->ss.st.out_bytes = sk.len; e->ss.st.combined_crc = e->ss.combined_crc;
@@ -387,6 +453,7 @@ int bz2b200_compress_device(bz2b200_engine* h, const void* d_src, size_t src_len
    EngineFull* e = reinterpret_cast<EngineFull*>(h);
    if (!e || !d_dst || !dst_len || (!d_src && src_len) || ((uintptr_t)d_dst & 3)) return set_err(BZ2B200_EPARAM, "bad argument");
    DeviceGuard guard(e->device);
+   e->after_s1 = nullptr;
    stream_reset(e);
    StreamState& ss = e->ss;
    u8* out = static_cast<u8*>(d_dst);
@@ -437,6 +504,7 @@ int bz2b200_stream_feed(bz2b200_engine* h, const void* src, size_t n, int end_mo
    if (!e || !sink || (!src && n) || end_mode < 0 || end_mode > 2) return set_err(BZ2B200_EPARAM, "bad argument");
    if (!e->h_in) return set_err(BZ2B200_EPARAM, "bz2b200_stream_begin was not called");
    DeviceGuard guard(e->device);
+   e->after_s1 = nullptr;
    StreamState& ss = e->ss;
    Sink sk; sk.fn = sink; sk.user = user; sk.dst = nullptr; sk.cap = 0; sk.len = 0;
    int rc;
