@@ -68,7 +68,7 @@ static void engine_free(EngineFull* e)
    cudaSetDevice(e->device);
    void* dev[] = { e->enc, e->cend, e->sa, e->rank, e->keyA, e->keyB, e->idxB, e->bwt, e->z, e->mtfv, e->hist,
                    e->blockmap, e->code, e->kk, e->nbins, e->hh, e->kbits, e->ksym, e->K, e->kscrA, e->kscrB, e->tile_len, e->tile_ext, e->tile_carry, e->tile_size, e->tile_base, e->s1_scalars,
-                   e->mtf_summary, e->mtf_tilemeta, e->mtf_tilecnt, e->sel, e->hlen, e->hfreq, e->hcode, e->grpbits,
+                   e->mtf_summary, e->mtf_tilemeta, e->mtf_tilecnt, e->mtf_mode, e->sel, e->hlen, e->hfreq, e->hcode, e->grpbits,
                    e->pre, e->prebits, e->ngroups, e->d_in, e->d_out,
                    e->bt.X, e->bt.P, e->bt.crc, e->bt.origptr, e->bt.power_q, e->bt.inuse, e->bt.ninuse, e->bt.nmtf,
                    e->bt.mtffreq, e->bt.bits, e->bt.bitoff, e->lists.counts[0], e->lists.counts[1] };
@@ -145,7 +145,7 @@ static int engine_new(EngineFull** out, int device, int level, size_t window_byt
       ALLOC(e->s1_scalars, 16);
       ALLOC(e->mtf_summary, B * tiles_max * 256);
       ALLOC(e->mtf_tilemeta, B * tiles_max * 5);
-      ALLOC(e->mtf_tilecnt, B * tiles_max);
+      ALLOC(e->mtf_tilecnt, B * tiles_max); ALLOC(e->mtf_mode, B);
       ALLOC(e->sel, E / 50 + 2 * B + 64);
       ALLOC(e->grpbits, E / 50 + 2 * B + 64);
       ALLOC(e->hlen, B * 6 * BZ_MAX_ALPHA); ALLOC(e->hfreq, B * 6 * BZ_MAX_ALPHA); ALLOC(e->hcode, B * 6 * BZ_MAX_ALPHA);

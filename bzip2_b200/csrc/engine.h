@@ -105,6 +105,7 @@ struct Engine {
    // stage-3 scratch
    u8  *mtf_summary;       // [tiles*256] recency lists per tile, then start lists
    u32 *mtf_tilemeta;      // [blk_cap*tiles_max*5] lead, trail, inner, out_base | carry
+   u32 *mtf_mode;          // [blk_cap] which MTF kernel handles the block
    u32 *mtf_tilecnt;       // [blk_cap*tiles_max] distinct symbols per tile
    // stage-4 scratch
    u8  *sel;               // [E/50 + nb] selectors

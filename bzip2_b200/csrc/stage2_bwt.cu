@@ -516,6 +516,7 @@ __global__ void __launch_bounds__(LG_THREADS) k_refine_large(S2Params p, ListsDe
    __shared__ u32 binbase[TEXT ? LG_MAXPASS : 3][256];
    __shared__ u32 ssm[34];
    __shared__ u32 s_carry;
+   __shared__ u32 s_skip;
    const u64 entry = items[blockIdx.x];
    const u32 pos = (u32)(entry >> 32);
    const u32 b = (u32)(entry >> 20) & 0xfffu;
@@ -538,24 +539,33 @@ __global__ void __launch_bounds__(LG_THREADS) k_refine_large(S2Params p, ListsDe
       for (int q = 0; q < npass; q++) atomicAdd(&binbase[q][(u32)(key >> (8 * q)) & 255], 1u);
    }
    __syncthreads();
+   if (threadIdx.x == 0) s_skip = 0;
+   __syncthreads();
    if (w < (u32)npass) {
-      // exclusive scan of 256 bins by one warp: 8 per lane
+      // exclusive scan of 256 bins by one warp: 8 per lane.  A digit on which every key agrees
+      // (one bin holds the whole segment -- the rule on periodic data) needs no pass at all.
       u32 v[8], s = 0;
+      bool whole = false;
 #pragma unroll
-      for (int k = 0; k < 8; k++) { v[k] = binbase[w][l * 8 + k]; s += v[k]; }
+      for (int k = 0; k < 8; k++) { v[k] = binbase[w][l * 8 + k]; s += v[k]; whole |= (v[k] == len); }
+      if (__any_sync(FULL, whole) && l == 0) atomicOr(&s_skip, 1u << w);
       u32 ex = warp_incl_sum(s) - s;
 #pragma unroll
       for (int k = 0; k < 8; k++) { binbase[w][l * 8 + k] = ex; ex += v[k]; }
    }
    __syncthreads();
+   const u32 skip = s_skip;
 
    // phase B: passes
+   int done = 0;                                   // passes actually executed (selects the ping-pong side)
    for (int pass = 0; pass < npass; pass++) {
-      const KT* ksrc = (pass & 1) ? kB : kA;
-      const u32* isrc = (pass & 1) ? p.idxB : p.sa;
-      KT* kdst = (pass & 1) ? kA : kB;
-      u32* idst = (pass & 1) ? p.sa : p.idxB;
+      if ((skip >> pass) & 1u) continue;
+      const KT* ksrc = (done & 1) ? kB : kA;
+      const u32* isrc = (done & 1) ? p.idxB : p.sa;
+      KT* kdst = (done & 1) ? kA : kB;
+      u32* idst = (done & 1) ? p.sa : p.idxB;
       const int shift = pass * 8;
+      done++;
       for (u32 tb = 0; tb < len; tb += LG_TILE) {
 #pragma unroll
          for (int k = 0; k < 8; k++) whist[w][l * 8 + k] = 0;
@@ -603,8 +613,8 @@ __global__ void __launch_bounds__(LG_THREADS) k_refine_large(S2Params p, ListsDe
       __threadfence_block();
    }
    // phase C: group boundaries, new ranks, next-round segments
-   const KT* kfin = (npass & 1) ? kB : kA;
-   const u32* ifin = (npass & 1) ? p.idxB : p.sa;
+   const KT* kfin = (done & 1) ? kB : kA;
+   const u32* ifin = (done & 1) ? p.idxB : p.sa;
    const bool deep = (depth >= n);
    if (threadIdx.x == 0) s_carry = 0;
    __syncthreads();
@@ -637,7 +647,7 @@ __global__ void __launch_bounds__(LG_THREADS) k_refine_large(S2Params p, ListsDe
          bool is_end = false;
          if (in) {
             const u32 idx = ifin[pos + i];
-            if (npass & 1) p.sa[pos + i] = idx;
+            if (done & 1) p.sa[pos + i] = idx;
             p.rank[xb + idx] = rk_pack(round + 1, pos - xb, (pos - xb) + g);
             is_end = (i == len - 1) || (kk[k + 2] != kk[k + 1]);
          }
