@@ -22,7 +22,7 @@ class Stats(C.Structure):
                 ("n_windows", C.c_uint32), ("sum_nblock", C.c_uint64), ("sum_nmtf", C.c_uint64),
                 ("n_power_blocks", C.c_uint32), ("combined_crc", C.c_uint32),
                 ("ms_total", C.c_float), ("ms_s1", C.c_float), ("ms_s2", C.c_float), ("ms_s3", C.c_float),
-                ("ms_s4", C.c_float), ("bwt_rounds", C.c_uint32), ("kernel_launches", C.c_uint32)]
+                ("ms_s4", C.c_float), ("bwt_rounds", C.c_uint32), ("kernel_launches", C.c_uint32), ("out_bits", C.c_uint64)]
 
 
 class BzStream(C.Structure):
@@ -44,6 +44,7 @@ EXPORTS = [
     "bz2b200_device_count", "bz2b200_last_error", "bz2b200_version", "bz2b200_engine_create",
     "bz2b200_engine_destroy", "bz2b200_engine_set_stream", "bz2b200_compress_host", "bz2b200_compress_device", "bz2b200_stream_begin",
     "bz2b200_stream_feed", "bz2b200_debug_keep", "bz2b200_debug_fetch",
+    "bz2b200_scan_create", "bz2b200_scan_boundary", "bz2b200_scan_destroy", "bz2b200_concat_bits",
     # include/bzlib.h
     "BZ2_bzCompressInit", "BZ2_bzCompress", "BZ2_bzCompressEnd", "BZ2_bzBuffToBuffCompress",
     "BZ2_bzWriteOpen", "BZ2_bzWrite", "BZ2_bzWriteClose", "BZ2_bzWriteClose64", "BZ2_bzlibVersion",
@@ -75,6 +76,14 @@ def load():
     lib.bz2b200_debug_keep.argtypes = [vp, C.c_int]
     lib.bz2b200_debug_fetch.restype = C.c_int
     lib.bz2b200_debug_fetch.argtypes = [vp, C.c_char_p, vp, sz, C.POINTER(sz)]
+    lib.bz2b200_scan_create.restype = C.c_int
+    lib.bz2b200_scan_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, vp, sz, C.c_int, C.c_uint64, C.c_int]
+    lib.bz2b200_scan_boundary.restype = C.c_int
+    lib.bz2b200_scan_boundary.argtypes = [vp, sz, sz, C.c_uint, C.POINTER(sz), C.POINTER(C.c_uint32)]
+    lib.bz2b200_scan_destroy.restype = None
+    lib.bz2b200_scan_destroy.argtypes = [vp]
+    lib.bz2b200_concat_bits.restype = C.c_int
+    lib.bz2b200_concat_bits.argtypes = [C.c_int, vp, C.c_uint64, vp, C.c_uint64]
     lib.BZ2_bzCompressInit.restype = C.c_int
     lib.BZ2_bzCompressInit.argtypes = [C.POINTER(BzStream), C.c_int, C.c_int, C.c_int]
     lib.BZ2_bzCompress.restype = C.c_int

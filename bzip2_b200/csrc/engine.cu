@@ -461,9 +461,13 @@ int bz2b200_compress_device(bz2b200_engine* h, const void* d_src, size_t src_len
    const size_t need = src_len + src_len / 64 + (src_len / e->nmax + 2) * 24576 + 64;
    if (dst_cap < need) return set_err(BZ2B200_EOUTFULL, "device destination too small (need src_len*1.016 + 24 KiB per block)");
    BZ_CUDA(e, cudaMemsetAsync(out, 0, dst_cap & ~(size_t)3, e->stream));
-   int rc = put_bits_device(e, out, 0, 0, 0x425A6830u + (u32)e->level, 32);
-   if (rc) return rc;
-   ss.bits = 32; ss.header_done = true;
+   int rc = 0;
+   if (!(flags & BZ2B200_NO_HEADER)) {
+      rc = put_bits_device(e, out, 0, 0, 0x425A6830u + (u32)e->level, 32);
+      if (rc) return rc;
+      ss.bits = 32;
+   }
+   ss.header_done = true;
    const u8* in = static_cast<const u8*>(d_src);
    const bool tail_merge = !(flags & BZ2B200_TAIL_STREAMED);
    size_t pos = 0;
@@ -476,10 +480,13 @@ int bz2b200_compress_device(bz2b200_engine* h, const void* d_src, size_t src_len
       if (cons == 0) return set_err(BZ2B200_EINTERNAL, "window made no progress");
       pos += cons;
    }
-   if ((rc = put_bits_device(e, out, 0, ss.bits, 0x177245385090ULL, 48))) return rc;
-   ss.bits += 48;
-   if ((rc = put_bits_device(e, out, 0, ss.bits, ss.combined_crc, 32))) return rc;
-   ss.bits += 32;
+   if (!(flags & BZ2B200_NO_TRAILER)) {
+      if ((rc = put_bits_device(e, out, 0, ss.bits, 0x177245385090ULL, 48))) return rc;
+      ss.bits += 48;
+      if ((rc = put_bits_device(e, out, 0, ss.bits, ss.combined_crc, 32))) return rc;
+      ss.bits += 32;
+   }
+   ss.st.out_bits = ss.bits;
    BZ_CUDA(e, cudaStreamSynchronize(e->stream));
    *dst_len = (size_t)((ss.bits + 7) >> 3);
    ss.st.in_bytes = src_len; ss.st.out_bytes = *dst_len; ss.st.combined_crc = ss.combined_crc;
@@ -542,6 +549,79 @@ int bz2b200_engine_set_stream(bz2b200_engine* h, void* cuda_stream)
    EngineFull* e = reinterpret_cast<EngineFull*>(h);
    if (!e) return set_err(BZ2B200_EPARAM, "null engine");
    e->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : e->own_stream;
+   return 0;
+}
+
+struct bz2b200_scan { ScanState s; };
+
+void bz2b200_scan_destroy(bz2b200_scan* h)
+{
+   if (!h) return;
+   ScanState& s = h->s;
+   DeviceGuard guard(s.device);
+   void* dev[] = { s.tile_len, s.tile_ext, s.tile_carry, s.tile_size, s.tile_base, s.cend, s.scal, s.q };
+   for (void* p : dev) if (p) cudaFree(p);
+   if (s.h_scal) cudaFreeHost(s.h_scal);
+   if (s.st) cudaStreamDestroy(s.st);
+   free(h);
+}
+
+int bz2b200_scan_create(bz2b200_scan** out, int device, int level, const void* d_src, size_t n,
+                        int prev_byte, uint64_t prev_run, int input_ends)
+{
+   if (!out || level < 1 || level > 9 || (!d_src && n) || n >= 0xfff00000ull) return set_err(BZ2B200_EPARAM, "bad argument");
+   int ndev = 0;
+   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return set_err(BZ2B200_ENODEV, "no such CUDA device");
+   bz2b200_scan* h = static_cast<bz2b200_scan*>(calloc(1, sizeof(bz2b200_scan)));
+   if (!h) return set_err(BZ2B200_ENOMEM, "out of host memory");
+   ScanState& s = h->s;
+   DeviceGuard guard(device);
+   s.device = device; s.nmax = 100000u * (u32)level - 19u;
+   s.in = static_cast<const u8*>(d_src); s.W = (u32)n; s.input_ends = input_ends ? 1u : 0u;
+   s.prev_byte = (prev_byte >= 0 && prev_byte < 256 && prev_run) ? (u32)prev_byte : 256u;
+   s.carry0 = (s.prev_byte < 256) ? (u32)(prev_run % 255u) : 0u;
+   const size_t nt = n / 4096 + 4;
+   s.cend_cap = n + n / 4 + 4096;
+   bool ok = cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) == cudaSuccess;
+   ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.tile_len), nt * 4) == cudaSuccess;
+   ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.tile_ext), nt * 4) == cudaSuccess;
+   ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.tile_carry), nt * 4) == cudaSuccess;
+   ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.tile_size), nt * 4) == cudaSuccess;
+   ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.tile_base), nt * 4) == cudaSuccess;
+   ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.cend), s.cend_cap) == cudaSuccess;
+   ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.scal), 16 * 4) == cudaSuccess;
+   ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.q), 2 * 4) == cudaSuccess;
+   ok = ok && cudaMallocHost(reinterpret_cast<void**>(&s.h_scal), 16 * 4) == cudaSuccess;
+   if (!ok) { cudaGetLastError(); bz2b200_scan_destroy(h); return set_err(BZ2B200_ENOMEM, "scan allocation failed"); }
+   cudaMemsetAsync(s.scal, 0, 16 * 4, s.st);
+   const int rc = n ? scan_build(&s, s.prev_byte, s.carry0) : 0;
+   if (rc) { bz2b200_scan_destroy(h); return set_err(BZ2B200_ECUDA, "shard scan failed"); }
+   *out = h;
+   return 0;
+}
+
+int bz2b200_scan_boundary(bz2b200_scan* h, size_t start, size_t limit, unsigned flags, size_t* boundary, uint32_t* n_blocks)
+{
+   if (!h || !boundary || start > h->s.W) return set_err(BZ2B200_EPARAM, "bad argument");
+   ScanState& s = h->s;
+   DeviceGuard guard(s.device);
+   if (limit > s.W) limit = s.W;
+   if (start >= limit) { *boundary = start; if (n_blocks) *n_blocks = 0; return 0; }
+   u32 b = 0, nb = 0;
+   const int rc = scan_boundary(&s, (u32)start, (u32)limit, (flags & BZ2B200_TAIL_STREAMED) ? 0u : 1u, &b, &nb);
+   if (rc == -3) return set_err(BZ2B200_EOUTFULL, "block chain ran past the scanned data (halo too small)");
+   if (rc) return set_err(BZ2B200_ECUDA, "boundary chain failed");
+   *boundary = b;
+   if (n_blocks) *n_blocks = nb;
+   return 0;
+}
+
+int bz2b200_concat_bits(int device, void* d_dst, uint64_t dst_bit, const void* d_src, uint64_t nbits)
+{
+   if (!d_dst || (!d_src && nbits) || ((uintptr_t)d_dst & 3) || ((uintptr_t)d_src & 3)) return set_err(BZ2B200_EPARAM, "bad argument");
+   DeviceGuard guard(device);
+   const int rc = concat_bits_device(static_cast<u8*>(d_dst), dst_bit, static_cast<const u8*>(d_src), nbits);
+   if (rc) return set_err(BZ2B200_ECUDA, "concat_bits failed");
    return 0;
 }
 

@@ -59,12 +59,28 @@ struct BlockTables {                        // per-window block metadata (device
 
 struct Engine;
 
+// One shard's chunk structure for the multi-GPU boundary chain (stage1_rle.cu)
+struct ScanState {
+   int device; u32 nmax; cudaStream_t st;
+   const u8* in; u32 W; u32 input_ends;
+   u32 prev_byte, carry0;
+   u32 ntiles, enc_total;
+   u32 *tile_len, *tile_ext, *tile_carry, *tile_size, *tile_base;
+   u8* cend; size_t cend_cap;
+   u32* scal;     // [16] device scalars
+   u32* q;        // [2] device queries
+   u32* h_scal;   // [16] pinned
+};
+int scan_build(ScanState* s, u32 prev_byte, u32 carry0);
+int scan_boundary(ScanState* s, u32 start, u32 limit, u32 tail_merge, u32* boundary, u32* nblocks);
+
 // ---- stage launchers (each returns 0 or a negative error; all work on e->stream) ----
 int stage1_run(Engine* e, const u8* d_in, u32 W, bool is_final, bool tail_merge, u32* nb_out, u32* consumed_out, u32* enc_total_out);
 int stage2_run(Engine* e, u32 nb, u32 E);
 int stage3_run(Engine* e, u32 nb, u32 E);
 int stage4_run(Engine* e, u32 nb, u32 E, u8* d_out, u64 origin_bit, u64 start_bit, u64* end_bit_out);
 int put_bits_device(Engine* e, u8* d_out, u64 origin_bit, u64 bitpos, u64 value, int nbits);
+int concat_bits_device(u8* d_dst, u64 dst_bit, const u8* d_src, u64 nbits);
 
 struct Engine {
    int device;

@@ -17,6 +17,7 @@
 //   k_tile<FIND>     map each block's encoded start back to its input position
 //   k_crc            block CRCs: per-thread table CRC, GF(2) shift-combine, atomicXor
 #include "engine.h"
+#include <string.h>
 
 namespace bz {
 
@@ -24,7 +25,7 @@ constexpr int S1_THREADS = 256;
 constexpr int S1_BPT = 16;
 constexpr int S1_TILE = S1_THREADS * S1_BPT;   // 4096
 
-enum { S1_AGG = 0, S1_COUNT = 1, S1_SCATTER = 2, S1_FIND = 3 };
+enum { S1_AGG = 0, S1_COUNT = 1, S1_SCATTER = 2, S1_FIND = 3, S1_LOCATE = 4 };
 
 struct RunAgg { u32 len; u32 ext; };   // ext: every position so far continues the run entering the range
 __device__ __forceinline__ RunAgg run_comb(RunAgg a, RunAgg b)
@@ -69,8 +70,11 @@ struct S1Params {
    u32 is_final;
    u32* tile_len; u32* tile_ext; u32* tile_carry; u32* tile_size; u32* tile_base;
    u8* enc; u8* cend;
-   const u32* X; u32* P; u32 nb_find;   // FIND mode
+   const u32* X; u32* P; u32 nb_find;   // FIND mode: encoded offsets X[1..] -> input positions P[1..]
    const u32* scalars;                   // [2] = enc_total
+   u32 prev_byte;       // byte before in[0] (256: none) and the length of the run it ends,
+   u32 carry0;          // when the window does not start at a chunk boundary (shard scans)
+   const u32* Q; u32* EQ;                // LOCATE mode: input positions Q[k] -> encoded offsets EQ[k]
 };
 
 template <int MODE>
@@ -102,6 +106,12 @@ __global__ void __launch_bounds__(S1_THREADS) k_tile(S1Params p)
       __syncthreads();
       tile = s_tile;
    }
+   u32 locQ = 0;
+   if (MODE == S1_LOCATE) {
+      locQ = p.Q[blockIdx.x];
+      if (locQ >= p.W) { if (threadIdx.x == 0) p.EQ[blockIdx.x] = p.scalars[2]; return; }
+      tile = (locQ + align) / S1_TILE;
+   }
    const i64 pos0 = (i64)tile * S1_TILE + (i64)threadIdx.x * S1_BPT - (i64)align;   // window position of c[0]
    u8 c[S1_BPT];
    {
@@ -118,6 +128,7 @@ __global__ void __launch_bounds__(S1_THREADS) k_tile(S1Params p)
    }
    u32 prevb = 256, nextb = 256;
    if (pos0 >= 1 && pos0 - 1 < (i64)p.W) prevb = p.in[pos0 - 1];
+   else if (pos0 == 0) prevb = p.prev_byte;
    if (pos0 + S1_BPT >= 0 && pos0 + S1_BPT < (i64)p.W) nextb = p.in[pos0 + S1_BPT];
 
    // per-position "continues the run" flags and the thread aggregate
@@ -128,7 +139,7 @@ __global__ void __launch_bounds__(S1_THREADS) k_tile(S1Params p)
       i64 q = pos0 + k;
       bool valid = (q >= 0 && q < (i64)p.W);
       u32 pb = (k == 0) ? prevb : (u32)c[k - 1];
-      if (k > 0 && q == 0) pb = 256;                       // window position 0 never continues a run
+      if (k > 0 && q == 0) pb = p.prev_byte;               // 256 unless the window continues a run (shard scans)
       bool eq = valid && (pb == (u32)c[k]);
       if (valid) {
          vmask |= 1u << k;
@@ -152,7 +163,7 @@ __global__ void __launch_bounds__(S1_THREADS) k_tile(S1Params p)
    for (int k = 0; k < 16; k++) {
       if (!((vmask >> k) & 1)) { ph[k] = 0xffff; continue; }
       if ((eqmask >> k) & 1) {
-         if (k == 0) j = rbefore % 255u; else { j = j + 1; if (j == 255) j = 0; }
+         if (k == 0 || pos0 + k == 0) j = rbefore % 255u; else { j = j + 1; if (j == 255) j = 0; }
       } else j = 0;
       // careful: when k>0 and previous position was invalid (before window) j restarts at 0 via eq=false
       ph[k] = j;
@@ -180,26 +191,32 @@ __global__ void __launch_bounds__(S1_THREADS) k_tile(S1Params p)
          E += (jj < 3) ? 1u : (jj == 3 ? 2u : 0u);
          continue;
       }
+      if (MODE == S1_LOCATE) {
+         if ((u32)q == locQ) p.EQ[blockIdx.x] = E;
+         E += (jj < 3) ? 1u : (jj == 3 ? 2u : 0u);
+         continue;
+      }
+      const bool wr = (p.enc != nullptr);                  // shard scans only need the chunk-end flags
       if (jj < 3) {
-         p.enc[E] = (u8)ch;
+         if (wr) p.enc[E] = (u8)ch;
          if (last) p.cend[E] = 1;
          E += 1;
       } else if (jj == 3) {
-         p.enc[E] = (u8)ch;
-         if (last) { p.enc[E + 1] = 0; p.cend[E + 1] = 1; }
+         if (wr) p.enc[E] = (u8)ch;
+         if (last) { if (wr) p.enc[E + 1] = 0; p.cend[E + 1] = 1; }
          E += 2;
       } else {
-         if (last) { p.enc[E - 1] = (u8)(jj - 3); p.cend[E - 1] = 1; }
+         if (last) { if (wr) p.enc[E - 1] = (u8)(jj - 3); p.cend[E - 1] = 1; }
       }
    }
 }
 
 // Segmented scan of tile aggregates: carry[t] = run length ending just before tile t.
-__global__ void __launch_bounds__(1024) k_scan_runs(const u32* tile_len, const u32* tile_ext, u32* carry, u32 ntiles)
+__global__ void __launch_bounds__(1024) k_scan_runs(const u32* tile_len, const u32* tile_ext, u32* carry, u32 ntiles, u32 carry0)
 {
    __shared__ RunAgg wsm[32];
    __shared__ RunAgg s_run;
-   if (threadIdx.x == 0) { s_run.len = 0; s_run.ext = 1; }
+   if (threadIdx.x == 0) { s_run.len = carry0; s_run.ext = 1; }
    __syncthreads();
    const u32 l = lane_id(), w = threadIdx.x >> 5;
    for (u32 base = 0; base < ntiles; base += 1024) {
@@ -376,9 +393,10 @@ int stage1_run(Engine* e, const u8* d_in, u32 W, bool is_final, bool tail_merge,
    p.tile_len = e->tile_len; p.tile_ext = e->tile_ext; p.tile_carry = e->tile_carry;
    p.tile_size = e->tile_size; p.tile_base = e->tile_base;
    p.enc = e->enc; p.cend = e->cend; p.X = e->bt.X; p.P = e->bt.P; p.nb_find = 0; p.scalars = e->s1_scalars;
+   p.prev_byte = 256; p.carry0 = 0; p.Q = nullptr; p.EQ = nullptr;
 
    k_tile<S1_AGG><<<ntiles, S1_THREADS, 0, st>>>(p);                                   BZ_KCHECK(e);
-   k_scan_runs<<<1, 1024, 0, st>>>(e->tile_len, e->tile_ext, e->tile_carry, ntiles);   BZ_KCHECK(e);
+   k_scan_runs<<<1, 1024, 0, st>>>(e->tile_len, e->tile_ext, e->tile_carry, ntiles, 0);   BZ_KCHECK(e);
    k_tile<S1_COUNT><<<ntiles, S1_THREADS, 0, st>>>(p);                                 BZ_KCHECK(e);
    k_scan_u32<<<1, 1024, 0, st>>>(e->tile_size, e->tile_base, ntiles, e->s1_scalars + 2); BZ_KCHECK(e);
    BZ_CUDA(e, cudaMemcpyAsync(e->h_scalars, e->s1_scalars, 4 * sizeof(u32), cudaMemcpyDeviceToHost, st));
@@ -401,6 +419,89 @@ int stage1_run(Engine* e, const u8* d_in, u32 W, bool is_final, bool tail_merge,
    BZ_CUDA(e, cudaMemcpyAsync(e->h_scalars + 8, e->bt.P + nb, sizeof(u32), cudaMemcpyDeviceToHost, st));
    BZ_CUDA(e, cudaStreamSynchronize(st));
    *consumed_out = e->h_scalars[8];
+   return 0;
+}
+
+
+// ---- shard scan (multi-GPU sharding of one stream by block) ---------------------------
+// The chunk structure of a shard (cend flags, encoded offsets) does not depend on where blocks
+// start, so every GPU can build it in parallel; only the greedy walk from the previous GPU's last
+// boundary is serial, and that walk is one dependent load per block.
+__global__ void k_chain_from(const u8* cend, const u32* scal_in, u32* out, u32 nmax, u32 input_ends, u32 tail_merge)
+{
+   // scal_in[0] = encoded offset of the start boundary, [1] = encoded offset of the limit, [2] = total
+   const u32 l = lane_id();
+   const u32 Etot = scal_in[2];
+   const u32 xlim = scal_in[1];
+   u32 x = scal_in[0];
+   u32 nblk = 0;
+   while (x < xlim) {
+      const u32 target = x + nmax - 1;
+      if (target >= Etot) { x = input_ends ? Etot : 0xffffffffu; nblk++; break; }
+      const u32 e = target + l;
+      const bool f = (l < 8) && (e < Etot) && (cend[e] != 0);
+      const u32 m = __ballot_sync(FULL, f);
+      if (m == 0) { x = input_ends ? Etot : 0xffffffffu; nblk++; break; }
+      u32 nx = target + (u32)(__ffs(m) - 1) + 1;
+      if (input_ends && tail_merge && Etot - nx == 1) nx = Etot;
+      x = nx; nblk++;
+   }
+   if (l == 0) { out[0] = x; out[1] = nblk; }
+}
+
+int scan_build(ScanState* s, u32 prev_byte, u32 carry0)
+{
+   cudaStream_t st = s->st;
+   const u32 align = (u32)((uintptr_t)s->in & 15);
+   s->ntiles = (s->W + align + S1_TILE - 1) / S1_TILE;
+   S1Params p;
+   memset(&p, 0, sizeof p);
+   p.in = s->in; p.W = s->W; p.is_final = s->input_ends;
+   p.tile_len = s->tile_len; p.tile_ext = s->tile_ext; p.tile_carry = s->tile_carry;
+   p.tile_size = s->tile_size; p.tile_base = s->tile_base;
+   p.enc = nullptr; p.cend = s->cend; p.scalars = s->scal;
+   p.prev_byte = prev_byte; p.carry0 = carry0;
+   k_tile<S1_AGG><<<s->ntiles, S1_THREADS, 0, st>>>(p);
+   k_scan_runs<<<1, 1024, 0, st>>>(s->tile_len, s->tile_ext, s->tile_carry, s->ntiles, carry0);
+   k_tile<S1_COUNT><<<s->ntiles, S1_THREADS, 0, st>>>(p);
+   k_scan_u32<<<1, 1024, 0, st>>>(s->tile_size, s->tile_base, s->ntiles, s->scal + 2);
+   if (cudaMemcpyAsync(s->h_scal, s->scal, 4 * sizeof(u32), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+   if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+   s->enc_total = s->h_scal[2];
+   if ((u64)s->enc_total + 16 > s->cend_cap) return -2;
+   if (cudaMemsetAsync(s->cend, 0, (size_t)s->enc_total + 16, st) != cudaSuccess) return -1;
+   k_tile<S1_SCATTER><<<s->ntiles, S1_THREADS, 0, st>>>(p);
+   if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+   return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// first block boundary >= limit when blocks are laid greedily from the boundary `start`
+int scan_boundary(ScanState* s, u32 start, u32 limit, u32 tail_merge, u32* boundary, u32* nblocks)
+{
+   cudaStream_t st = s->st;
+   S1Params p;
+   memset(&p, 0, sizeof p);
+   p.in = s->in; p.W = s->W; p.is_final = s->input_ends;
+   p.tile_len = s->tile_len; p.tile_ext = s->tile_ext; p.tile_carry = s->tile_carry;
+   p.tile_size = s->tile_size; p.tile_base = s->tile_base;
+   p.enc = nullptr; p.cend = s->cend; p.scalars = s->scal;
+   p.prev_byte = s->prev_byte; p.carry0 = s->carry0;
+   p.Q = s->q; p.EQ = s->scal + 4;            // scal[4] = E(start), scal[5] = E(limit)
+   s->h_scal[8] = start; s->h_scal[9] = limit;
+   if (cudaMemcpyAsync(s->q, s->h_scal + 8, 2 * sizeof(u32), cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
+   k_tile<S1_LOCATE><<<2, S1_THREADS, 0, st>>>(p);
+   // chain input: [0]=E(start) [1]=E(limit) [2]=total  -> reuse scal+4.. as a 3-vector
+   if (cudaMemcpyAsync(s->scal + 6, s->scal + 2, sizeof(u32), cudaMemcpyDeviceToDevice, st) != cudaSuccess) return -1;
+   k_chain_from<<<1, 32, 0, st>>>(s->cend, s->scal + 4, s->scal + 10, s->nmax, s->input_ends, tail_merge);
+   // boundary (encoded) -> input position through the FIND mode: X[1] = scal[10]
+   p.X = s->scal + 9; p.P = s->scal + 12;      // X[1] = scal[10]; P[1] = scal[13]
+   k_tile<S1_FIND><<<1, S1_THREADS, 0, st>>>(p);
+   if (cudaMemcpyAsync(s->h_scal, s->scal, 16 * sizeof(u32), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+   if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+   if (cudaGetLastError() != cudaSuccess) return -1;
+   if (s->h_scal[10] == 0xffffffffu) return -3;         // ran off the data before reaching the limit: halo too small
+   *boundary = s->h_scal[13];
+   *nblocks = s->h_scal[11];
    return 0;
 }
 

@@ -434,6 +434,31 @@ __global__ void k_put_bits(u32* outw, u64 relbit, u64 value, int nbits)
    }
 }
 
+// S5 for shards: OR `nbits` bits of src (from its bit 0) into dst at bit offset dst_bit.
+// One thread per source word; each lands in at most two destination words.
+__global__ void __launch_bounds__(256) k_concat_bits(u32* dst, u64 dst_bit, const u32* src, u64 nbits)
+{
+   const u64 k = (u64)blockIdx.x * 256 + threadIdx.x;
+   const u64 nwords = (nbits + 31) >> 5;
+   if (k >= nwords) return;
+   u32 v = bswap32(src[k]);
+   const u64 left = nbits - k * 32;
+   if (left < 32) v &= ~((1u << (32 - (u32)left)) - 1u);
+   const u64 bp = dst_bit + k * 32;
+   const u32 sh = (u32)(bp & 31);
+   if (v >> sh) atomicOr(&dst[bp >> 5], bswap32(v >> sh));
+   if (sh && (v << (32 - sh))) atomicOr(&dst[(bp >> 5) + 1], bswap32(v << (32 - sh)));
+}
+
+int concat_bits_device(u8* d_dst, u64 dst_bit, const u8* d_src, u64 nbits)
+{
+   if (nbits == 0) return 0;
+   const u64 nwords = (nbits + 31) >> 5;
+   k_concat_bits<<<(unsigned)((nwords + 255) / 256), 256>>>(reinterpret_cast<u32*>(d_dst), dst_bit, reinterpret_cast<const u32*>(d_src), nbits);
+   if (cudaGetLastError() != cudaSuccess) return -1;
+   return cudaDeviceSynchronize() == cudaSuccess ? 0 : -1;
+}
+
 int put_bits_device(Engine* e, u8* d_out, u64 origin_bit, u64 bitpos, u64 value, int nbits)
 {
    k_put_bits<<<1, 1, 0, e->stream>>>(reinterpret_cast<u32*>(d_out), bitpos - origin_bit, value, nbits);

@@ -47,6 +47,11 @@ typedef struct bz2b200_engine bz2b200_engine;
                                      final byte joins a block that has just filled
                                      (bzlib.c:276-308)                                         */
 
+/* Segment mode (one stream sharded by block over several GPUs, see bz2b200_scan_*): the call
+ * emits only its blocks, starting at bit 0 of the destination; the caller places the pieces. */
+#define BZ2B200_NO_HEADER     2u
+#define BZ2B200_NO_TRAILER    4u
+
 typedef struct {
    uint64_t in_bytes, out_bytes;
    uint32_t n_blocks, n_windows;
@@ -57,6 +62,7 @@ typedef struct {
    float    ms_total, ms_s1, ms_s2, ms_s3, ms_s4;   /* CUDA-event times, summed over windows */
    uint32_t bwt_rounds;          /* prefix-doubling rounds, summed over windows              */
    uint32_t kernel_launches;
+   uint64_t out_bits;            /* exact bit length of what was produced (segment mode: not padded)   */
 } bz2b200_stats;
 
 int  bz2b200_device_count(void);
@@ -85,6 +91,24 @@ typedef int (*bz2b200_sink)(void* user, const void* bytes, size_t n);
 int  bz2b200_stream_begin(bz2b200_engine* e);
 int  bz2b200_stream_feed(bz2b200_engine* e, const void* src, size_t n, int end_mode,
                          bz2b200_sink sink, void* user);
+
+/* ---- sharding one stream by block over several GPUs --------------------------------
+ * Blocks are independent once their boundaries are known, and boundaries are a greedy chain over
+ * the RLE1 chunk structure (bzlib.c:227, :383).  Each GPU scans its shard (plus a halo of the next
+ * shard) in parallel; the chain itself is one integer handed from GPU g to GPU g+1.
+ *   scan_create   chunk structure of d_src[0,n).  prev_byte / prev_run: the byte before d_src[0]
+ *                 and the length of the run it ends (256 / 0 at the start of the stream);
+ *                 input_ends: the stream ends at n.
+ *   scan_boundary first block boundary >= limit when blocks are laid from the boundary `start`;
+ *                 also the number of blocks in [start, boundary).
+ *   concat_bits   S5: OR `nbits` bits of d_src (from bit 0) into d_dst at bit offset dst_bit.     */
+typedef struct bz2b200_scan bz2b200_scan;
+int  bz2b200_scan_create(bz2b200_scan** out, int device, int block_size_100k, const void* d_src, size_t n,
+                         int prev_byte, uint64_t prev_run, int input_ends);
+int  bz2b200_scan_boundary(bz2b200_scan* s, size_t start, size_t limit, unsigned flags,
+                           size_t* boundary, uint32_t* n_blocks);
+void bz2b200_scan_destroy(bz2b200_scan* s);
+int  bz2b200_concat_bits(int device, void* d_dst, uint64_t dst_bit, const void* d_src, uint64_t nbits);
 
 /* Per-stage intermediates of the LAST window processed (tests only).
  * name: "X" "P" "crc" "origptr" "power_q" "inuse" "ninuse" "nmtf" "mtffreq" "bits" "bitoff"

@@ -345,8 +345,11 @@ void orc_send_mtf(const uint16_t* mtfv, int32_t n_mtf, const uint8_t* in_use,
 }
 
 /* ---------------------------------------------------------- whole stream -- */
-int64_t orc_compress(const uint8_t* in, uint64_t n, int level, int tail_merge,
-                     const int32_t* force_orig_ptr, uint8_t* out, uint64_t out_cap)
+/* flags: 2 = no stream header, 4 = no trailer (segment of a sharded stream).  *bits_out gets the
+ * exact bit length, *fold_out the combined-CRC fold of this call's blocks started from 0. */
+int64_t orc_compress_ex(const uint8_t* in, uint64_t n, int level, int tail_merge, unsigned flags,
+                        const int32_t* force_orig_ptr, uint8_t* out, uint64_t out_cap,
+                        uint64_t* bits_out, uint32_t* fold_out, uint32_t* nblocks_out)
 {
    int64_t max_blocks = (int64_t)(n / (uint64_t)(100000 * level - 19 - 5)) + 2;
    orc_block* blocks = malloc(sizeof(orc_block) * (size_t)max_blocks);
@@ -358,7 +361,7 @@ int64_t orc_compress(const uint8_t* in, uint64_t n, int level, int tail_merge,
    uint8_t* bwt = malloc(900000 + 16);
    uint16_t* mtfv = malloc(sizeof(uint16_t) * (900000 + 16));
    uint32_t comb = 0;
-   put_bits(out, &bp, 24, 0x425A68); put_bits(out, &bp, 8, (uint32_t)('0' + level));   /* compress.c:841-845 */
+   if (!(flags & 2u)) { put_bits(out, &bp, 24, 0x425A68); put_bits(out, &bp, 8, (uint32_t)('0' + level)); }   /* compress.c:841-845 */
    for (int64_t b = 0; b < nb; b++) {
       uint8_t in_use[256];
       int32_t freq[258], nu, op;
@@ -376,8 +379,46 @@ int64_t orc_compress(const uint8_t* in, uint64_t n, int level, int tail_merge,
       put_bits(out, &bp, 24, (uint32_t)op);
       orc_send_mtf(mtfv, nm, in_use, freq, out, &bp);
    }
-   put_bits(out, &bp, 24, 0x177245); put_bits(out, &bp, 24, 0x385090);                   /* compress.c:872-880 */
-   put_bits(out, &bp, 16, comb >> 16); put_bits(out, &bp, 16, comb & 0xffff);
+   if (!(flags & 4u)) {
+      put_bits(out, &bp, 24, 0x177245); put_bits(out, &bp, 24, 0x385090);                /* compress.c:872-880 */
+      put_bits(out, &bp, 16, comb >> 16); put_bits(out, &bp, 16, comb & 0xffff);
+   }
+   if (bits_out) *bits_out = bp;
+   if (fold_out) *fold_out = comb;
+   if (nblocks_out) *nblocks_out = (uint32_t)nb;
    free(blocks); free(blk); free(bwt); free(mtfv);
    return (int64_t)((bp + 7) >> 3);
+}
+
+int64_t orc_compress(const uint8_t* in, uint64_t n, int level, int tail_merge,
+                     const int32_t* force_orig_ptr, uint8_t* out, uint64_t out_cap)
+{
+   return orc_compress_ex(in, n, level, tail_merge, 0, force_orig_ptr, out, out_cap, 0, 0, 0);
+}
+
+/* First block boundary >= limit when blocks are laid greedily from the boundary `start`
+ * (bzlib.c:227, :383); n_blocks = blocks in [start, boundary).  Returns n if the input ends first
+ * (input_ends) or UINT64_MAX if more data is needed. */
+uint64_t orc_find_boundary(const uint8_t* in, uint64_t n, uint64_t start, uint64_t limit, int level,
+                           int tail_merge, int input_ends, uint32_t* n_blocks)
+{
+   const int32_t nmax = 100000 * level - 19;
+   uint64_t pos = start, bnd = start;
+   int32_t fill = 0;
+   uint32_t nb = 0;
+   while (bnd < limit) {
+      if (pos >= n) { if (!input_ends) return UINT64_MAX; if (fill) nb++; bnd = n; break; }
+      uint8_t ch = in[pos];
+      int len = 1;
+      while (pos + len < n && len < 255 && in[pos + len] == ch) len++;
+      if (pos + len == n && !input_ends && len < 255) return UINT64_MAX;   /* chunk may continue in unseen data */
+      pos += len;
+      fill += chunk_cost(len);
+      if (fill >= nmax) {
+         if (input_ends && tail_merge && pos + 1 == n) pos = n;
+         bnd = pos; fill = 0; nb++;
+      }
+   }
+   if (n_blocks) *n_blocks = nb;
+   return bnd;
 }

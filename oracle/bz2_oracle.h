@@ -69,6 +69,14 @@ int64_t orc_compress(const uint8_t* in, uint64_t n, int level, int tail_merge,
                      const int32_t* force_orig_ptr,
                      uint8_t* out, uint64_t out_cap);
 
+/* Segment form of orc_compress (flags: 2 = no header, 4 = no trailer) and the block-boundary
+ * chain, used to check the multi-GPU sharding logic on the CPU. */
+int64_t orc_compress_ex(const uint8_t* in, uint64_t n, int level, int tail_merge, unsigned flags,
+                        const int32_t* force_orig_ptr, uint8_t* out, uint64_t out_cap,
+                        uint64_t* bits_out, uint32_t* fold_out, uint32_t* nblocks_out);
+uint64_t orc_find_boundary(const uint8_t* in, uint64_t n, uint64_t start, uint64_t limit, int level,
+                           int tail_merge, int input_ends, uint32_t* n_blocks);
+
 #ifdef __cplusplus
 }
 #endif

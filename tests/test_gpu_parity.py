@@ -261,3 +261,79 @@ def test_large_text_roundtrip_and_accounting(engine_for):
     for blk in S.orc_split(d, 9):
         comb = (((comb << 1) | (comb >> 31)) & 0xFFFFFFFF) ^ blk.crc
     assert st.combined_crc == comb
+
+
+# ------------------------------------------------------------------ multi-rank sharding of one stream
+def test_scan_boundary_matches_oracle():
+    from bzip2_b200 import sharding as sh
+    be = sh.GpuBackend(1, 0)
+    ob = sh.OracleBackend(1)
+    data = np.concatenate([S.gen_text(300_000), np.full(200_000, 9, np.uint8), S.gen_random(150_000), S.gen_runs(900_000, seed=8)])
+    reg = be.load(data)
+    scan = be.scan(reg, 256, 0, True)
+    start = 0
+    while start < data.size:
+        for limit in (start + 1, start + 150_000, data.size):
+            got = be.boundary(scan, start, min(limit, data.size), False)
+            exp = ob.boundary((data, True), start, min(limit, data.size), False)
+            assert got == exp, (start, limit, got, exp)
+        start = got[0] if got[0] > start else data.size
+    be.free_scan(scan)
+    be.eng.close()
+
+
+def test_concat_bits_matches_numpy():
+    import torch
+    from bzip2_b200 import sharding as sh
+    be = sh.GpuBackend(1, 0)
+    rng = np.random.default_rng(3)
+    dst = be.new_stream(4096)
+    ref = np.zeros(dst.numel(), np.uint8)
+    bit = 0
+    for k in range(40):
+        nbits = int(rng.integers(1, 700))
+        src = rng.integers(0, 256, (nbits + 7) // 8 + 8, dtype=np.uint8)
+        srcp = np.zeros((src.size + 3) & ~3, np.uint8)
+        srcp[: src.size] = src
+        be.place(dst, bit, torch.from_numpy(srcp).cuda(), nbits)
+        sh.or_bits(ref, bit, src, nbits)
+        bit += nbits
+    assert np.array_equal(dst.cpu().numpy()[:4096], ref[:4096])
+
+
+@pytest.mark.parametrize("world,level,gen", [(2, 9, "mixed"), (3, 9, "text"), (4, 1, "mixed"), (3, 9, "runs"), (3, 9, "fb")])
+def test_sharded_stream_equals_single(engine_for, world, level, gen):
+    from bzip2_b200 import sharding as sh
+    data = {"mixed": lambda: S.gen_mixed(23_000_000, seg=1 << 21), "text": lambda: S.gen_text(17_000_000),
+            "runs": lambda: S.gen_runs(260_000_000, seed=4),
+            "fb": lambda: np.full(150_000_001, 251, np.uint8)}[gen]()       # every shard starts inside the same run
+    single = engine_for(level).compress(data)
+    shards = [np.ascontiguousarray(data[r * data.size // world:(r + 1) * data.size // world]) for r in range(world)]
+    halos = sh.make_halos(shards, 64 << 20)
+    backends = {}
+
+    def make(r):
+        backends[r] = sh.GpuBackend(level, 0)
+        return backends[r]
+    out, infos = sh.run_threads(world, make, shards, halos, level)
+    for b in backends.values():
+        b.eng.close()
+    assert out == single
+    assert sum(i["blocks"] for i in infos) == engine_for(level).stats.n_blocks
+
+
+def test_cli_matches_oracle(tmp_path):
+    import subprocess
+    cli = os.path.join(os.path.dirname(B.LIB_PATH), "bzip2-b200")
+    data = S.gen_mixed(1_300_000, seg=1 << 17).tobytes()
+    src = tmp_path / "input.dat"
+    src.write_bytes(data)
+    r = subprocess.run([cli, "-3", "-k", str(src)], capture_output=True)
+    assert r.returncode == 0, r.stderr
+    got = (tmp_path / "input.dat.bz2").read_bytes()
+    assert got == S.orc_compress(data, 3, tail_merge=0)          # CLI feeds every byte in BZ_RUN mode
+    assert src.exists()
+    r = subprocess.run([cli, "-3", "-c"], input=data, capture_output=True)
+    assert r.returncode == 0 and r.stdout == got
+    r = subprocess.run([cli, "-3", "-k", str(src)], capture_output=True)    # refuses to overwrite
+    assert r.returncode != 0 and b"already exists" in r.stderr
