@@ -119,6 +119,89 @@ def cpu_reference_rate(data, level, threads, seconds_budget, sample_bytes):
     return per * threads / dt / 1e6, kind, f"{per * threads} B prefix of the workload as {threads} independent slice(s), -{level}, one pass, {dt:.1f} s"
 
 
+def sharded_bench(args, torch, dist, B, rank, world, local_rank, dev, data, n, metric, config):
+    """N > 1: ONE .bz2 stream, sharded by block across the ranks (bzip2_b200/sharding.py): every rank scans
+    its shard (+ halo) for chunk ends, the block-boundary chain is one integer handed rank to rank, every rank
+    compresses its block-aligned segment, rank 0 bit-shifts the pieces into place over NVLink (S5)."""
+    from bzip2_b200 import sharding as sh
+    halo_bytes = min(n, 64 << 20)
+    halo = make_input(args.workload, halo_bytes, rank + 1) if rank + 1 < world else np.zeros(0, np.uint8)
+    region_h = torch.from_numpy(np.concatenate([data, halo])).pin_memory()
+    be = sh.GpuBackend(args.level, local_rank)
+    comm = sh.TorchComm(dist, dev)
+    ends = rank == world - 1
+    region_d = region_h.to(dev)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def one(resident):
+        reg = region_d if resident else region_h.to(dev, non_blocking=True)
+        out, info = sh.compress_sharded(be, comm, reg, n, args.level, ends, return_host=not resident)
+        return out, info
+
+    for _ in range(args.warmup):
+        out, info = one(True)
+    barrier()
+    t0 = time.perf_counter()
+    with ClockSampler(local_rank) as clk:
+        for _ in range(args.steps):
+            out, info = one(True)
+        barrier()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_per_step = float(tt.item()) / args.steps * 1e3
+    value = world * n / (ms_per_step * 1e-3) / 1e6
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(max(1, min(args.warmup, 2))):
+            host_out, info = one(False)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            host_out, info = one(False)
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": round(world * n * args.steps / float(tt.item()) / 1e6, 2), "unit": "MB/s",
+               "h2d_bytes_per_step": int(region_h.numel()), "d2h_bytes_per_step": int(info["total_bytes"]) if rank == 0 else 0,
+               "api": "bzip2_b200.sharding.compress_sharded over bz2b200_scan_* / bz2b200_compress_device / bz2b200_concat_bits, pinned host buffers"}
+        if rank == 0:
+            import bz2 as _bz2
+            # the assembled stream is one valid .bz2 stream: decode its head with an independent decoder
+            d = _bz2.BZ2Decompressor()
+            head = d.decompress(bytes(host_out[: 4 << 20]), max_length=1 << 20)
+            assert head == data[: len(head)].tobytes(), "sharded stream does not decode to the input"
+    st = be.eng.stats
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:  # noqa: BLE001
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        seg_in = info["segment"][1] - info["segment"][0]
+        s2_bytes = 2.0 * st.sum_nblock
+        roof = {"bound": "hbm", "kernel": "S2 BWT stage of rank 0 (k-gram bucket + prefix-doubling kernels)",
+                "achieved": round(s2_bytes / (st.ms_s2 * 1e-3) / 1e9, 3), "peak": peak, "unit": "GB/s",
+                "frac": round(s2_bytes / (st.ms_s2 * 1e-3) / 1e9 / peak, 6), "traffic": None,
+                "stage_ms_rank0": {"s1": round(st.ms_s1, 3), "s2": round(st.ms_s2, 3), "s3": round(st.ms_s3, 3), "s4": round(st.ms_s4, 3)},
+                "rank0_segment_bytes": int(seg_in)}
+        config = dict(config)
+        config["workload"] += f"; ONE stream of {world} x {args.mb} MB sharded by block, 64 MiB halo per rank"
+        line = {"metric": metric, "value": round(value, 2), "unit": "MB/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config, "clocks": clk.summary(),
+                "e2e": e2e, "gpu_launches": int(st.kernel_launches), "roofline": roof, "cpu_baseline": None,
+                "out_bytes": int(info["total_bytes"]), "blocks_rank0": int(st.n_blocks)}
+        print(json.dumps(line))
+    dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -179,6 +262,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     data = make_input(args.workload, n, rank)
+    if world > 1:
+        return sharded_bench(args, torch, dist, B, rank, world, local_rank, dev, data, n, metric, config)
     h_in = torch.from_numpy(data).pin_memory()
     d_in = h_in.to(dev)
     cap = n + n // 50 + 24576 * (n // (100000 * args.level - 19) + 2) + 1024

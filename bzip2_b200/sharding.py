@@ -202,7 +202,12 @@ class GpuBackend:
             raise self.binding.Bz2B200Error(f"concat_bits rc={rc}: {self.lib.bz2b200_last_error().decode()}")
 
     def to_host(self, stream, nbytes):
-        return stream[:nbytes].cpu().numpy().tobytes()
+        # pinned staging buffer, reused between calls; the result is a read-only view of it
+        if getattr(self, "_pin", None) is None or self._pin.numel() < nbytes:
+            self._pin = self.torch.empty(nbytes + (nbytes >> 4) + 4096, dtype=self.torch.uint8).pin_memory()
+        self._pin[:nbytes].copy_(stream[:nbytes], non_blocking=True)
+        self.torch.cuda.current_stream(self.dev).synchronize()
+        return memoryview(self._pin.numpy())[:nbytes]
 
 
 # ------------------------------------------------------------------------------------ protocol

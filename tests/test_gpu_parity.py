@@ -318,7 +318,7 @@ def test_sharded_stream_equals_single(engine_for, world, level, gen):
     out, infos = sh.run_threads(world, make, shards, halos, level)
     for b in backends.values():
         b.eng.close()
-    assert out == single
+    assert bytes(out) == single
     assert sum(i["blocks"] for i in infos) == engine_for(level).stats.n_blocks
 
 
