@@ -321,18 +321,24 @@ __device__ __forceinline__ u32 gf_xpow8(const u32* pw, u64 m)
 }
 
 constexpr int CRC_THREADS = 256;
-constexpr int CRC_CTAS_PER_BLOCK = 64;
+constexpr int CRC_CTAS_PER_BLOCK = 16;
 
 __global__ void __launch_bounds__(CRC_THREADS) k_crc(const u8* in, const u32* P, u32* crc_acc)
 {
-   __shared__ u32 tab[256];
+   __shared__ u32 tab[4][256];       // slicing-by-4: tab[k][b] = crc0 of byte b followed by k zero bytes
    __shared__ u32 pw[40];
    __shared__ u32 red[CRC_THREADS];
    {
       u32 r = threadIdx.x << 24;
 #pragma unroll
       for (int k = 0; k < 8; k++) r = (r & 0x80000000u) ? (r << 1) ^ 0x04C11DB7u : (r << 1);
-      tab[threadIdx.x] = r;
+      tab[0][threadIdx.x] = r;
+   }
+   __syncthreads();
+   for (int k = 1; k < 4; k++) {
+      const u32 v = tab[k - 1][threadIdx.x];
+      tab[k][threadIdx.x] = (v << 8) ^ tab[0][v >> 24];
+      __syncthreads();
    }
    if (threadIdx.x == 0) {
       u32 v = 0x100;                              // x^8
@@ -354,7 +360,14 @@ __global__ void __launch_bounds__(CRC_THREADS) k_crc(const u8* in, const u32* P,
    i64 ps = pe - (i64)s;                                                      // piece start
    if (ps < (i64)lo) ps = (i64)lo;
    u32 c = 0;
-   for (i64 q = ps; q < pe; q++) c = (c << 8) ^ tab[(c >> 24) ^ in[q]];
+   i64 q = ps;
+   for (; q < pe && ((uintptr_t)(in + q) & 3); q++) c = (c << 8) ^ tab[0][(c >> 24) ^ in[q]];
+   for (; q + 4 <= pe; q += 4) {
+      const u32 w = *reinterpret_cast<const u32*>(in + q);          // little-endian load: first byte is the low one
+      const u32 x = c ^ __byte_perm(w, 0, 0x0123);
+      c = tab[3][x >> 24] ^ tab[2][(x >> 16) & 0xff] ^ tab[1][(x >> 8) & 0xff] ^ tab[0][x & 0xff];
+   }
+   for (; q < pe; q++) c = (c << 8) ^ tab[0][(c >> 24) ^ in[q]];
    red[threadIdx.x] = c;
    __syncthreads();
    // tree combine: v[t] = v[t] * x^(8*s*2^k) ^ v[t + 2^k]

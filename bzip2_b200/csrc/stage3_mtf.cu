@@ -370,26 +370,41 @@ __global__ void __launch_bounds__(128) k_rle2_emit(S3Params p)
       u16* out = p.mtfv + (size_t)xb + b + m[3];
       u32 run = p.tcarry[(size_t)b * p.tiles_max + t];
       u32 o = 0;
-      for (u32 i = 0; i < size; i++) {
-         const u32 v = p.z[start + i];
-         if (v == 0) { run++; continue; }
-         if (run) {
-            u32 zz = run - 1;
-            for (;;) { const u32 s = zz & 1; out[o++] = (u16)s; atomicAdd(&hist[s], 1u); if (zz < 2) break; zz = (zz - 2) >> 1; }
-            run = 0;
+      u32 c0 = 0, c1 = 0, c2 = 0, c3 = 0;          // the hottest symbols are counted in registers
+      // the tile is read as aligned 32-bit words (all tiles of a block share the misalignment)
+      const u32 a = start & 3u;
+      const u32* in32 = reinterpret_cast<const u32*>(p.z + (start - a));
+      const u32 nwords = (size + a + 3) >> 2;
+      for (u32 w = 0; w < nwords; w++) {
+         const u32 word = in32[w];
+#pragma unroll
+         for (int k = 0; k < 4; k++) {
+            const i32 i = (i32)(w * 4 + k) - (i32)a;
+            if (i < 0 || i >= (i32)size) continue;
+            const u32 v = (word >> (8 * k)) & 0xff;
+            if (v == 0) { run++; continue; }
+            if (run) {
+               u32 zz = run - 1;
+               for (;;) { const u32 s = zz & 1; out[o++] = (u16)s; if (s) c1++; else c0++; if (zz < 2) break; zz = (zz - 2) >> 1; }
+               run = 0;
+            }
+            out[o++] = (u16)(v + 1);
+            if (v == 1) c2++; else if (v == 2) c3++; else atomicAdd(&hist[v + 1], 1u);
          }
-         out[o++] = (u16)(v + 1);
-         atomicAdd(&hist[v + 1], 1u);
       }
       if (t == ntile - 1) {
          if (run) {
             u32 zz = run - 1;
-            for (;;) { const u32 s = zz & 1; out[o++] = (u16)s; atomicAdd(&hist[s], 1u); if (zz < 2) break; zz = (zz - 2) >> 1; }
+            for (;;) { const u32 s = zz & 1; out[o++] = (u16)s; if (s) c1++; else c0++; if (zz < 2) break; zz = (zz - 2) >> 1; }
          }
          const u32 eob = p.ninuse[b] + 1;
          out[o++] = (u16)eob;
          atomicAdd(&hist[eob], 1u);
       }
+      if (c0) atomicAdd(&hist[0], c0);
+      if (c1) atomicAdd(&hist[1], c1);
+      if (c2) atomicAdd(&hist[2], c2);
+      if (c3) atomicAdd(&hist[3], c3);
    }
    __syncthreads();
    for (u32 k = threadIdx.x; k < BZ_MAX_ALPHA; k += 128)

@@ -223,12 +223,30 @@ struct BitW {
    __device__ u32 finish() { const u32 bits = nbytes * 8 + nacc; if (nacc) out[nbytes++] = (u8)(acc >> 56); return bits; }
 };
 
+__device__ __forceinline__ u32 bswap32(u32 v) { return __byte_perm(v, 0, 0x0123); }
+
+// Bit writer that ORs whole 32-bit words into a zeroed buffer, starting at any bit offset, so
+// several writers can fill disjoint bit ranges of the same buffer concurrently.
+struct BitWA {
+   u32* w; u64 acc; u32 nacc; u32 widx;
+   __device__ void init(u32* words, u32 startbit) { w = words; widx = startbit >> 5; nacc = startbit & 31; acc = 0; }
+   __device__ void put(u32 nb, u32 v)
+   {
+      acc |= (u64)v << (64 - nacc - nb);
+      nacc += nb;
+      if (nacc >= 32) { atomicOr(&w[widx++], bswap32((u32)(acc >> 32))); acc <<= 32; nacc -= 32; }
+   }
+   __device__ void finish() { if (nacc && (u32)(acc >> 32)) atomicOr(&w[widx], bswap32((u32)(acc >> 32))); }
+};
+
 // ---- codes, selectors, tables -> preamble bits; coded size (one CTA per block) ------------
 __global__ void __launch_bounds__(192) k_huff_finish(S4Params p)
 {
    __shared__ u32 cnt[6][24];
    __shared__ u32 basec[6][24];
    __shared__ u64 s_pay[6];
+   __shared__ u32 s_scan[34];
+   __shared__ u32 s_misc[4];
    const u32 b = blockIdx.x;
    const u32 t = threadIdx.x >> 5, l = lane_id();
    const u32 ng = p.ngroups[b];
@@ -264,53 +282,109 @@ __global__ void __launch_bounds__(192) k_huff_finish(S4Params p)
       }
    }
    __syncthreads();
-   if (threadIdx.x != 0) return;
-   // ---- serial part: header fields, symbol map, selectors, tables ----
-   BitW w; w.init(p.pre + (size_t)b * PRE_STRIDE);
-   const u32 crc = p.crc[b];
-   w.put(24, 0x314159); w.put(24, 0x265359);                        // compress.c:849-850
-   w.put(16, crc >> 16); w.put(16, crc & 0xffff);                   // :853
-   w.put(1, 0);                                                      // :864
-   w.put(24, p.origptr[b]);                                          // :866
+   // ---- preamble bits.  Three writers work on disjoint bit ranges of the zeroed buffer through
+   // atomicOr: thread 0 the fixed header + symbol map, all threads the selectors (their MTF
+   // positions are computed in parallel from last-occurrence times), thread 32 the tables.
+   u32* const prew = reinterpret_cast<u32*>(p.pre + (size_t)b * PRE_STRIDE);
    const u8* iu = p.inuse + (size_t)b * 256;
+   const u32 nsel = (nmtf + BZ_G_SIZE - 1) / BZ_G_SIZE;
+   const u8* selp = p.sel + sel_base(xb, b);
+   // header length: 48 + 32 + 1 + 24 magic/crc/rand/origPtr, 16 + 16 * ranges map, 3 + 15 counts
+   if (threadIdx.x < 32) {
+      u32 any = 0;
+      if (threadIdx.x < 16) for (int j = 0; j < 16; j++) any |= iu[threadIdx.x * 16 + j];
+      const u32 bal = __ballot_sync(FULL, any != 0);
+      if (threadIdx.x == 0) s_misc[0] = 105u + 16u + 16u * (u32)__popc(bal & 0xffffu) + 18u;
+   }
+   // selector MTF in parallel (compress.c:573-631): position = number of tables used more recently
+   const u32 per = (nsel + 191) / 192;
+   const u32 lo = threadIdx.x * per, hi = min(nsel, lo + per);
+   u32 lastv[6] = {0, 0, 0, 0, 0, 0};                  // 0 = not seen in my chunk; else index + 8
+   for (u32 g = lo; g < hi; g++) lastv[selp[g]] = g + 8;
+   u32 startv[6];
+#pragma unroll
+   for (int v = 0; v < 6; v++) {
+      const u32 incl = block_incl_max<192>(lastv[v], s_scan);
+      u32 prev = __shfl_up_sync(FULL, incl, 1);
+      if (l == 0) prev = s_scan[t];
+      startv[v] = max(prev, 7u - (u32)v);             // before the first selector the order is 0,1,2,3,4,5
+      __syncthreads();
+   }
+   u32 mybits = 0;
    {
+      u32 cur[6];
+#pragma unroll
+      for (int v = 0; v < 6; v++) cur[v] = startv[v];
+      for (u32 g = lo; g < hi; g++) {
+         const u32 sv = selp[g];
+         u32 mine = 0, pos = 0;
+#pragma unroll
+         for (int v = 0; v < 6; v++) if ((u32)v == sv) mine = cur[v];
+#pragma unroll
+         for (int v = 0; v < 6; v++) pos += (cur[v] > mine) ? 1u : 0u;
+         mybits += pos + 1;
+#pragma unroll
+         for (int v = 0; v < 6; v++) if ((u32)v == sv) cur[v] = g + 8;
+      }
+   }
+   u32 selbits_total;
+   const u32 myoff = block_excl_sum<192>(mybits, s_scan, &selbits_total);
+   const u32 hdrbits = s_misc[0];
+   {
+      BitWA w; w.init(prew, hdrbits + myoff);
+      u32 cur[6];
+#pragma unroll
+      for (int v = 0; v < 6; v++) cur[v] = startv[v];
+      for (u32 g = lo; g < hi; g++) {
+         const u32 sv = selp[g];
+         u32 mine = 0, pos = 0;
+#pragma unroll
+         for (int v = 0; v < 6; v++) if ((u32)v == sv) mine = cur[v];
+#pragma unroll
+         for (int v = 0; v < 6; v++) pos += (cur[v] > mine) ? 1u : 0u;
+         w.put(pos + 1, (1u << (pos + 1)) - 2u);                       // :686-688  pos ones then a zero
+#pragma unroll
+         for (int v = 0; v < 6; v++) if ((u32)v == sv) cur[v] = g + 8;
+      }
+      w.finish();
+   }
+   if (threadIdx.x == 0) {
+      BitWA w; w.init(prew, 0);
+      const u32 crc = p.crc[b];
+      w.put(24, 0x314159); w.put(24, 0x265359);                        // compress.c:849-850
+      w.put(16, crc >> 16); w.put(16, crc & 0xffff);                   // :853
+      w.put(1, 0);                                                      // :864
+      w.put(24, p.origptr[b]);                                          // :866
       u32 used16 = 0;
       for (int i = 0; i < 16; i++) { u32 any = 0; for (int j = 0; j < 16; j++) any |= iu[i * 16 + j]; used16 = (used16 << 1) | (any ? 1u : 0u); }
-      w.put(16, used16);                                             // :654-664
+      w.put(16, used16);                                                // :654-664
       for (int i = 0; i < 16; i++) if (used16 & (0x8000u >> i)) {
          u32 v = 0; for (int j = 0; j < 16; j++) v = (v << 1) | (iu[i * 16 + j] ? 1u : 0u);
-         w.put(16, v);                                               // :666-674
+         w.put(16, v);                                                  // :666-674
       }
+      w.put(3, ng); w.put(15, nsel);                                    // :681-682
+      w.finish();
    }
-   const u32 nsel = (nmtf + BZ_G_SIZE - 1) / BZ_G_SIZE;
-   w.put(3, ng); w.put(15, nsel);                                    // :681-682
-   {
-      const u8* selp = p.sel + sel_base(xb, b);
-      u32 order = 0x543210;                                          // nibble k = table at MTF position k
-      for (u32 g = 0; g < nsel; g++) {
-         const u32 s = selp[g];
-         u32 pos = 0;
-         while (((order >> (4 * pos)) & 0xf) != s) pos++;
-         const u32 lowmask = (1u << (4 * pos)) - 1u;
-         order = (order & ~((lowmask << 4) | 0xfu)) | ((order & lowmask) << 4) | s;
-         w.put(pos + 1, (1u << (pos + 1)) - 2u);                     // :686-688  pos ones then a zero
+   if (threadIdx.x == 32) {
+      BitWA w; w.init(prew, hdrbits + selbits_total);
+      u32 tb = 0;
+      for (u32 tt = 0; tt < ng; tt++) {                                 // :696-706
+         const u8* len = lenb + tt * BZ_MAX_ALPHA;
+         u32 cur = len[0];
+         w.put(5, cur); tb += 5;
+         for (u32 v = 0; v < alpha; v++) {
+            while (cur < len[v]) { w.put(2, 2); cur++; tb += 2; }
+            while (cur > len[v]) { w.put(2, 3); cur--; tb += 2; }
+            w.put(1, 0); tb += 1;
+         }
       }
+      w.finish();
+      const u32 pbits = hdrbits + selbits_total + tb;
+      p.prebits[b] = pbits;
+      u64 pay = 0;
+      for (u32 tt = 0; tt < ng; tt++) pay += s_pay[tt];
+      p.bits[b] = (u64)pbits + pay;
    }
-   for (u32 tt = 0; tt < ng; tt++) {                                 // :696-706
-      const u8* len = lenb + tt * BZ_MAX_ALPHA;
-      u32 cur = len[0];
-      w.put(5, cur);
-      for (u32 v = 0; v < alpha; v++) {
-         while (cur < len[v]) { w.put(2, 2); cur++; }
-         while (cur > len[v]) { w.put(2, 3); cur--; }
-         w.put(1, 0);
-      }
-   }
-   const u32 pbits = w.finish();
-   p.prebits[b] = pbits;
-   u64 pay = 0;
-   for (u32 tt = 0; tt < ng; tt++) pay += s_pay[tt];
-   p.bits[b] = (u64)pbits + pay;
 }
 
 // exclusive scan of block bit sizes from start_bit (one CTA); bitoff[nb] = end
@@ -354,8 +428,6 @@ __global__ void __launch_bounds__(1024) k_group_scan(S4Params p)
    u32 ex = block_excl_sum<1024>(sum, ssm, nullptr);
    for (u32 k = 0; k < per; k++) if (lo + k < nsel) { const u32 v = gb[lo + k]; gb[lo + k] = ex; ex += v; }
 }
-
-__device__ __forceinline__ u32 bswap32(u32 v) { return __byte_perm(v, 0, 0x0123); }
 
 // ---- payload: one thread per 50-symbol group, written at its final stream position ----------
 __global__ void __launch_bounds__(SEL_THREADS) k_pack(S4Params p, u32* outw, u64 origin_bit)
