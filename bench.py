@@ -352,9 +352,21 @@ def main():
     c = st.out_bytes / max(1, st.in_bytes)
     A = 1 + 4 * rho + 12 * rho * mu + 3 * c              # algorithmic bytes per input byte, whole pass
     s2_bytes = 2 * rho * n                               # BWT stage: read block once, write last column once
-    roof = {"bound": "hbm", "kernel": "S2 BWT stage (bigram bucket + prefix-doubling kernels)",
+    # DRAM traffic of the same stage from the committed ncu capture (profiles/r01_traffic.json), scaled to this step
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if args.workload == "text" and args.level == 9:
+            traffic = int(tr["per_input_byte"]["S2"]["dram_bytes"] * n)
+    except Exception:  # noqa: BLE001
+        pass
+    roof = {"bound": "hbm",
+            "kernel": "S2 BWT kernel family (k_kgram*, k_refine_*, k_bwt_out; ~65 launches per 100 MB window), timed live by CUDA events "
+                      "around the stage on the launching stream; top single kernel k_refine_large<true> = 12% of the step "
+                      "(profiles/r01_final_launch_summary_text100MB.md)",
+            "algorithmic_bytes": int(s2_bytes), "algorithmic_rule": "2*rho bytes per input byte: read the block once, write the last column once (SURVEY 8d)",
             "achieved": round(s2_bytes / (stage_ms[2] * 1e-3) / 1e9, 3), "peak": peak, "unit": "GB/s",
-            "frac": round(s2_bytes / (stage_ms[2] * 1e-3) / 1e9 / peak, 6), "traffic": None, "peak_source": peak_src,
+            "frac": round(s2_bytes / (stage_ms[2] * 1e-3) / 1e9 / peak, 6), "traffic": traffic, "peak_source": peak_src,
             "whole_pass": {"A_bytes_per_input_byte": round(A, 3), "rho": round(rho, 4), "mu": round(mu, 4), "c": round(c, 4),
                            "achieved": round(A * n / (stage_ms[0] * 1e-3) / 1e9, 3),
                            "frac": round(A * n / (stage_ms[0] * 1e-3) / 1e9 / peak, 6)},
