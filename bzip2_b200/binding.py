@@ -48,6 +48,9 @@ EXPORTS = [
     # include/bzlib.h
     "BZ2_bzCompressInit", "BZ2_bzCompress", "BZ2_bzCompressEnd", "BZ2_bzBuffToBuffCompress",
     "BZ2_bzWriteOpen", "BZ2_bzWrite", "BZ2_bzWriteClose", "BZ2_bzWriteClose64", "BZ2_bzlibVersion",
+    "BZ2_bzDecompressInit", "BZ2_bzDecompress", "BZ2_bzDecompressEnd", "BZ2_bzBuffToBuffDecompress",
+    "BZ2_bzReadOpen", "BZ2_bzReadClose", "BZ2_bzReadGetUnused", "BZ2_bzRead",
+    "BZ2_bzopen", "BZ2_bzdopen", "BZ2_bzread", "BZ2_bzwrite", "BZ2_bzflush", "BZ2_bzclose", "BZ2_bzerror",
 ]
 
 
@@ -93,6 +96,28 @@ def load():
     lib.BZ2_bzBuffToBuffCompress.restype = C.c_int
     lib.BZ2_bzBuffToBuffCompress.argtypes = [vp, C.POINTER(C.c_uint), vp, C.c_uint, C.c_int, C.c_int, C.c_int]
     lib.BZ2_bzlibVersion.restype = C.c_char_p
+    lib.BZ2_bzDecompressInit.restype = C.c_int
+    lib.BZ2_bzDecompressInit.argtypes = [C.POINTER(BzStream), C.c_int, C.c_int]
+    lib.BZ2_bzDecompress.restype = C.c_int
+    lib.BZ2_bzDecompress.argtypes = [C.POINTER(BzStream)]
+    lib.BZ2_bzDecompressEnd.restype = C.c_int
+    lib.BZ2_bzDecompressEnd.argtypes = [C.POINTER(BzStream)]
+    lib.BZ2_bzBuffToBuffDecompress.restype = C.c_int
+    lib.BZ2_bzBuffToBuffDecompress.argtypes = [vp, C.POINTER(C.c_uint), vp, C.c_uint, C.c_int, C.c_int]
+    lib.BZ2_bzopen.restype = vp
+    lib.BZ2_bzopen.argtypes = [C.c_char_p, C.c_char_p]
+    lib.BZ2_bzdopen.restype = vp
+    lib.BZ2_bzdopen.argtypes = [C.c_int, C.c_char_p]
+    lib.BZ2_bzread.restype = C.c_int
+    lib.BZ2_bzread.argtypes = [vp, vp, C.c_int]
+    lib.BZ2_bzwrite.restype = C.c_int
+    lib.BZ2_bzwrite.argtypes = [vp, vp, C.c_int]
+    lib.BZ2_bzflush.restype = C.c_int
+    lib.BZ2_bzflush.argtypes = [vp]
+    lib.BZ2_bzclose.restype = None
+    lib.BZ2_bzclose.argtypes = [vp]
+    lib.BZ2_bzerror.restype = C.c_char_p
+    lib.BZ2_bzerror.argtypes = [vp, C.POINTER(C.c_int)]
     lib.bz2b200_pool_clear.restype = None
     return lib
 
@@ -199,3 +224,44 @@ class bzlib:
 
     def end(self):
         return self.lib.BZ2_bzCompressEnd(C.byref(self.strm))
+
+
+def decompress_stream(data, in_chunk=1 << 16, out_chunk=1 << 16):
+    """Host decoder through BZ2_bzDecompressInit / BZ2_bzDecompress / BZ2_bzDecompressEnd.
+    Returns (rc, output bytes, input bytes left unread)."""
+    lib = load()
+    strm = BzStream()
+    rc = lib.BZ2_bzDecompressInit(C.byref(strm), 0, 0)
+    if rc != BZ_OK:
+        raise Bz2B200Error(f"BZ2_bzDecompressInit rc={rc}")
+    src = np.frombuffer(bytes(data), dtype=np.uint8).copy() if len(data) else np.zeros(1, np.uint8)
+    ob = np.empty(out_chunk, np.uint8)
+    out = bytearray()
+    pos = 0
+    rc = BZ_OK
+    while True:
+        take = min(in_chunk, len(data) - pos)
+        strm.next_in = src.ctypes.data + pos
+        strm.avail_in = take
+        while True:
+            strm.next_out = ob.ctypes.data
+            strm.avail_out = out_chunk
+            rc = lib.BZ2_bzDecompress(C.byref(strm))
+            out += ob[:out_chunk - strm.avail_out].tobytes()
+            if rc != BZ_OK or strm.avail_out > 0:
+                break
+        pos += take - strm.avail_in
+        if rc != BZ_OK or (strm.avail_in == 0 and pos >= len(data)):
+            break
+    lib.BZ2_bzDecompressEnd(C.byref(strm))
+    return rc, bytes(out), len(data) - pos
+
+
+def decompress(data, cap):
+    """BZ2_bzBuffToBuffDecompress. Returns (rc, bytes)."""
+    lib = load()
+    src = np.frombuffer(bytes(data), dtype=np.uint8).copy() if len(data) else np.zeros(1, np.uint8)
+    dst = np.empty(max(cap, 1), np.uint8)
+    n = C.c_uint(cap)
+    rc = lib.BZ2_bzBuffToBuffDecompress(dst.ctypes.data, C.byref(n), src.ctypes.data, len(data), 0, 0)
+    return rc, dst[:n.value].tobytes()

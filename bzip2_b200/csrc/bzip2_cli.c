@@ -1,8 +1,9 @@
 /*
- * bzip2_cli.c -- `bzip2` command-line front end, compression side, over the GPU library.
+ * bzip2_cli.c -- `bzip2` command-line front end over the GPU library.
  *
- * Mirrors the user-visible behaviour of the reference CLI in compress mode
- * (bzip2.c: flag parsing :1870-1934, compressStream :328-427, compress() :1132-1309):
+ * Mirrors the user-visible behaviour of the reference CLI
+ * (bzip2.c: flag parsing :1870-1934, compressStream :328-427, compress() :1132-1309,
+ *  uncompressStream :432-553, testStream :557-642, uncompress() :1313-1507):
  *   -1..-9 / --fast / --best, -z, -c, -k, -f, -q, -v, -s (clamps the level to 2,
  *   bzip2.c:1937-1938), BZIP2 / BZIP environment flags, "file" -> "file.bz2", refusal to
  *   overwrite without -f, refusal to write compressed data to a terminal, input removed
@@ -10,7 +11,10 @@
  * It feeds the libbz2-compatible stdio API (BZ2_bzWriteOpen / BZ2_bzWrite /
  * BZ2_bzWriteClose64), with 4 MiB reads instead of the reference's 5000-byte trickle
  * (bzip2.c:350-358) -- the stream bytes do not depend on the chunking.
- * Decompression (-d, -t) is outside this build: use the reference's bzip2 for that.
+ * -d / -t (and the bunzip2 / bzcat program names) run the library's host decoder
+ * (BZ2_bzReadOpen / BZ2_bzRead / BZ2_bzReadGetUnused): concatenated streams are decoded
+ * back to back, trailing garbage after a complete stream is ignored with a warning,
+ * exit status 2 reports corrupt input (bzip2.c:432-553).
  */
 #include "../../include/bzlib.h"
 #include <errno.h>
@@ -20,7 +24,8 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
-static int level = 9, to_stdout = 0, keep = 0, force = 0, quiet = 0, verbose = 0, small = 0;
+enum { OP_COMPRESS, OP_DECOMPRESS, OP_TEST };
+static int level = 9, to_stdout = 0, keep = 0, force = 0, quiet = 0, verbose = 0, small = 0, op = OP_COMPRESS;
 static const char* prog = "bzip2";
 
 static void usage(void)
@@ -28,7 +33,9 @@ static void usage(void)
    fprintf(stderr,
       "bzip2-b200, a GPU (sm_100a) block-sorting file compressor, stream-compatible with bzip2 1.0.6.\n\n"
       "   usage: %s [flags and input files in any order]\n\n"
-      "   -z --compress       compress (the only mode of this build)\n"
+      "   -z --compress       compress on the GPU (default)\n"
+      "   -d --decompress     decompress (host decoder)\n"
+      "   -t --test           test compressed file integrity\n"
       "   -k --keep           keep (don't delete) input files\n"
       "   -f --force          overwrite existing output files\n"
       "   -c --stdout         output to standard out\n"
@@ -73,6 +80,110 @@ static int compress_stream(FILE* in, FILE* out, const char* name, unsigned long 
    return 0;
 }
 
+/* Decodes every stream in `in`; out == NULL only tests.  0 ok, 1 i/o trouble, 2 corrupt input. */
+static int expand_stream(FILE* in, FILE* out, const char* name)
+{
+   enum { CHUNK = 1 << 16 };
+   static char obuf[CHUNK];
+   char carry[BZ_MAX_UNUSED];
+   int ncarry = 0, streams = 0, bzerr = BZ_OK;
+   for (;;) {
+      void* un; int nun, c;
+      BZFILE* bz = BZ2_bzReadOpen(&bzerr, in, verbose, small, carry, ncarry);
+      if (bz == NULL || bzerr != BZ_OK) { fprintf(stderr, "%s: %s: cannot start the decoder (libbz2 error %d)\n", prog, name, bzerr); return 1; }
+      streams++;
+      while (bzerr == BZ_OK) {
+         int n = BZ2_bzRead(&bzerr, bz, obuf, CHUNK);
+         if (bzerr == BZ_DATA_ERROR_MAGIC) break;
+         if ((bzerr == BZ_OK || bzerr == BZ_STREAM_END) && n > 0 && out) {
+            if (fwrite(obuf, 1, (size_t)n, out) != (size_t)n || ferror(out)) {
+               fprintf(stderr, "%s: %s: write error: %s\n", prog, name, strerror(errno));
+               BZ2_bzReadClose(&bzerr, bz);
+               return 1;
+            }
+         }
+      }
+      if (bzerr != BZ_STREAM_END) {
+         int e = bzerr;
+         BZ2_bzReadClose(&bzerr, bz);
+         if (e == BZ_DATA_ERROR_MAGIC) {
+            if (streams == 1) { fprintf(stderr, "%s: %s is not a bzip2 file.\n", prog, name); return 2; }
+            if (!quiet) fprintf(stderr, "\n%s: %s: trailing garbage after EOF ignored\n", prog, name);
+            break;
+         }
+         if (e == BZ_IO_ERROR) { fprintf(stderr, "%s: %s: read error: %s\n", prog, name, strerror(errno)); return 1; }
+         if (e == BZ_UNEXPECTED_EOF) fprintf(stderr, "%s: %s: file ends unexpectedly\n", prog, name);
+         else if (e == BZ_MEM_ERROR) { fprintf(stderr, "%s: out of memory\n", prog); return 1; }
+         else fprintf(stderr, "%s: %s: data integrity (CRC) error in data\n", prog, name);
+         return 2;
+      }
+      BZ2_bzReadGetUnused(&bzerr, bz, &un, &nun);
+      ncarry = nun;
+      if (nun > 0) memcpy(carry, un, (size_t)nun);
+      BZ2_bzReadClose(&bzerr, bz);
+      if (ncarry == 0) {
+         c = fgetc(in);
+         if (c == EOF) break;
+         ungetc(c, in);
+      }
+   }
+   if (ferror(in)) { fprintf(stderr, "%s: %s: read error: %s\n", prog, name, strerror(errno)); return 1; }
+   if (out && fflush(out) != 0) { fprintf(stderr, "%s: write error: %s\n", prog, strerror(errno)); return 1; }
+   if (verbose) fprintf(stderr, "  %s: %s\n", name, out ? "done" : "ok");
+   return 0;
+}
+
+/* "x.bz2" -> "x", "x.tbz2" -> "x.tar", anything else -> "x.out" (bzip2.c:1313-1345). */
+static int expanded_name(const char* name, char* dst, size_t cap)
+{
+   static const char* const from[] = { ".bz2", ".bz", ".tbz2", ".tbz" };
+   static const char* const to[] = { "", "", ".tar", ".tar" };
+   size_t L = strlen(name), k;
+   for (k = 0; k < 4; k++) {
+      size_t fl = strlen(from[k]);
+      if (L > fl && strcmp(name + L - fl, from[k]) == 0) {
+         snprintf(dst, cap, "%.*s%s", (int)(L - fl), name, to[k]);
+         return 1;
+      }
+   }
+   snprintf(dst, cap, "%s.out", name);
+   return 0;
+}
+
+static int expand_file(const char* name)
+{
+   char outname[4096];
+   struct stat st;
+   FILE *in, *out;
+   int rc;
+   if (strlen(name) + 5 > sizeof outname) { fprintf(stderr, "%s: file name too long: %s\n", prog, name); return 1; }
+   if (stat(name, &st) != 0) { fprintf(stderr, "%s: Can't open input file %s: %s.\n", prog, name, strerror(errno)); return 1; }
+   if (S_ISDIR(st.st_mode)) { fprintf(stderr, "%s: Input file %s is a directory.\n", prog, name); return 1; }
+   in = fopen(name, "rb");
+   if (!in) { fprintf(stderr, "%s: Can't open input file %s: %s.\n", prog, name, strerror(errno)); return 1; }
+   if (op == OP_TEST || to_stdout) {
+      rc = expand_stream(in, op == OP_TEST ? NULL : stdout, name);
+      fclose(in);
+      return rc;
+   }
+   if (!expanded_name(name, outname, sizeof outname) && !quiet)
+      fprintf(stderr, "%s: Can't guess original name for %s -- using %s\n", prog, name, outname);
+   if (!force && access(outname, F_OK) == 0) {
+      fprintf(stderr, "%s: Output file %s already exists.\n", prog, outname);
+      fclose(in);
+      return 1;
+   }
+   out = fopen(outname, "wb");
+   if (!out) { fprintf(stderr, "%s: Can't create output file %s: %s.\n", prog, outname, strerror(errno)); fclose(in); return 1; }
+   rc = expand_stream(in, out, name);
+   fclose(in);
+   if (fclose(out) != 0 && !rc) rc = 1;
+   if (rc) { remove(outname); return rc; }
+   chmod(outname, st.st_mode & 07777);
+   if (!keep) remove(name);
+   return 0;
+}
+
 static void report(const char* name, unsigned long long nin, unsigned long long nout)
 {
    if (!verbose) return;
@@ -89,6 +200,7 @@ static int do_file(const char* name)
    unsigned long long nin = 0, nout = 0;
    int rc;
    size_t L = strlen(name);
+   if (op != OP_COMPRESS) return expand_file(name);
    if (L + 5 > sizeof outname) { fprintf(stderr, "%s: file name too long: %s\n", prog, name); return 1; }
    if (stat(name, &st) != 0) { fprintf(stderr, "%s: Can't open input file %s: %s.\n", prog, name, strerror(errno)); return 1; }
    if (S_ISDIR(st.st_mode)) { fprintf(stderr, "%s: Input file %s is a directory.\n", prog, name); return 1; }
@@ -126,7 +238,9 @@ static int handle_flag(const char* a)
 {
    if (a[1] == '-') {
       if (!strcmp(a, "--stdout")) to_stdout = 1;
-      else if (!strcmp(a, "--compress")) {}
+      else if (!strcmp(a, "--compress")) op = OP_COMPRESS;
+      else if (!strcmp(a, "--decompress")) op = OP_DECOMPRESS;
+      else if (!strcmp(a, "--test")) op = OP_TEST;
       else if (!strcmp(a, "--keep")) keep = 1;
       else if (!strcmp(a, "--force")) force = 1;
       else if (!strcmp(a, "--quiet")) quiet = 1;
@@ -136,21 +250,21 @@ static int handle_flag(const char* a)
       else if (!strcmp(a, "--best")) level = 9;
       else if (!strcmp(a, "--repetitive-fast") || !strcmp(a, "--repetitive-best") || !strcmp(a, "--exponential")) {}
       else if (!strcmp(a, "--help")) { usage(); exit(0); }
-      else if (!strcmp(a, "--decompress") || !strcmp(a, "--test")) { fprintf(stderr, "%s: this build only compresses; use the reference bzip2 to decompress\n", prog); exit(1); }
       else { fprintf(stderr, "%s: Bad flag `%s'\n", prog, a); usage(); exit(1); }
       return 0;
    }
    for (const char* p = a + 1; *p; p++) {
       switch (*p) {
          case 'c': to_stdout = 1; break;
-         case 'z': break;
+         case 'z': op = OP_COMPRESS; break;
+         case 'd': op = OP_DECOMPRESS; break;
+         case 't': op = OP_TEST; break;
          case 'k': keep = 1; break;
          case 'f': force = 1; break;
          case 'q': quiet = 1; break;
          case 'v': verbose++; break;
          case 's': small = 1; break;
          case 'h': usage(); exit(0);
-         case 'd': case 't': fprintf(stderr, "%s: this build only compresses; use the reference bzip2 to decompress\n", prog); exit(1);
          case '1': case '2': case '3': case '4': case '5': case '6': case '7': case '8': case '9': level = *p - '0'; break;
          default: fprintf(stderr, "%s: Bad flag `%s'\n", prog, a); usage(); exit(1);
       }
@@ -173,6 +287,8 @@ int main(int argc, char** argv)
    int i, nfiles = 0, rc = 0, dashdash = 0;
    const char* slash = strrchr(argv[0], '/');
    prog = slash ? slash + 1 : argv[0];
+   if (strstr(prog, "unzip") || strstr(prog, "UNZIP")) op = OP_DECOMPRESS;
+   if (strstr(prog, "z2cat") || strstr(prog, "Z2CAT") || strstr(prog, "zcat") || strstr(prog, "ZCAT")) { op = OP_DECOMPRESS; to_stdout = 1; }
    env_flags("BZIP2");
    env_flags("BZIP");
    for (i = 1; i < argc; i++) {
@@ -180,6 +296,13 @@ int main(int argc, char** argv)
       if (!dashdash && argv[i][0] == '-' && argv[i][1]) handle_flag(argv[i]); else nfiles++;
    }
    if (verbose > 4) verbose = 4;
+   if (nfiles == 0 && op != OP_COMPRESS) {
+      if (op == OP_DECOMPRESS && isatty(fileno(stdin)) && !force) {
+         fprintf(stderr, "%s: I won't read compressed data from a terminal.\n%s: For help, type: `%s --help'.\n", prog, prog, prog);
+         return 1;
+      }
+      return expand_stream(stdin, op == OP_TEST ? NULL : stdout, "(stdin)");
+   }
    if (nfiles == 0) {
       unsigned long long nin = 0, nout = 0;
       if (isatty(fileno(stdout)) && !force) {
@@ -194,7 +317,7 @@ int main(int argc, char** argv)
    for (i = 1; i < argc; i++) {
       if (!dashdash && !strcmp(argv[i], "--")) { dashdash = 1; continue; }
       if (!dashdash && argv[i][0] == '-' && argv[i][1]) continue;
-      rc |= do_file(argv[i]);
+      { int r = do_file(argv[i]); if (r > rc) rc = r; }
    }
    return rc;
 }

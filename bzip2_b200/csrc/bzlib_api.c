@@ -375,3 +375,156 @@ void BZ2_bzWriteClose(int* bzerror, BZFILE* b, int abandon, unsigned int* nbytes
 {
    BZ2_bzWriteClose64(bzerror, b, abandon, nbytes_in, NULL, nbytes_out, NULL);
 }
+
+/* ---- stdio read side (bzlib.c:1150-1301); decoding runs on the host (bzlib_decode.c) --------- */
+static int at_eof(FILE* f)
+{
+   int c = fgetc(f);
+   if (c == EOF) return 1;
+   ungetc(c, f);
+   return 0;
+}
+
+BZFILE* BZ2_bzReadOpen(int* bzerror, FILE* f, int verbosity, int small, void* unused, int nUnused)
+{
+   wfile* bzf = NULL;
+   int ret;
+   SETERR(BZ_OK);
+   if (f == NULL || (small != 0 && small != 1) || verbosity < 0 || verbosity > 4 ||
+       (unused == NULL && nUnused != 0) || (unused != NULL && (nUnused < 0 || nUnused > BZ_MAX_UNUSED))) {
+      SETERR(BZ_PARAM_ERROR); return NULL;
+   }
+   if (ferror(f)) { SETERR(BZ_IO_ERROR); return NULL; }
+   bzf = (wfile*)malloc(sizeof(wfile));
+   if (!bzf) { SETERR(BZ_MEM_ERROR); return NULL; }
+   memset(bzf, 0, sizeof *bzf);
+   bzf->handle = f; bzf->writing = 0; bzf->last_err = BZ_OK;
+   if (nUnused > 0) memcpy(bzf->buf, unused, (size_t)nUnused);
+   ret = BZ2_bzDecompressInit(&bzf->strm, verbosity, small);
+   if (ret != BZ_OK) { wfile* t = bzf; bzf = NULL; SETERR(ret); free(t); return NULL; }
+   bzf->strm.avail_in = (unsigned int)nUnused;
+   bzf->strm.next_in = bzf->buf;
+   return bzf;
+}
+
+void BZ2_bzReadClose(int* bzerror, BZFILE* b)
+{
+   wfile* bzf = (wfile*)b;
+   SETERR(BZ_OK);
+   if (bzf == NULL) return;
+   if (bzf->writing) { SETERR(BZ_SEQUENCE_ERROR); return; }
+   (void)BZ2_bzDecompressEnd(&bzf->strm);
+   free(bzf);
+}
+
+int BZ2_bzRead(int* bzerror, BZFILE* b, void* buf, int len)
+{
+   wfile* bzf = (wfile*)b;
+   int ret;
+   SETERR(BZ_OK);
+   if (bzf == NULL || buf == NULL || len < 0) { SETERR(BZ_PARAM_ERROR); return 0; }
+   if (bzf->writing) { SETERR(BZ_SEQUENCE_ERROR); return 0; }
+   if (len == 0) return 0;
+   bzf->strm.avail_out = (unsigned int)len;
+   bzf->strm.next_out = (char*)buf;
+   for (;;) {
+      if (ferror(bzf->handle)) { SETERR(BZ_IO_ERROR); return 0; }
+      if (bzf->strm.avail_in == 0 && !at_eof(bzf->handle)) {
+         size_t n = fread(bzf->buf, 1, BZ_MAX_UNUSED, bzf->handle);
+         if (ferror(bzf->handle)) { SETERR(BZ_IO_ERROR); return 0; }
+         bzf->strm.avail_in = (unsigned int)n;
+         bzf->strm.next_in = bzf->buf;
+      }
+      ret = BZ2_bzDecompress(&bzf->strm);
+      if (ret != BZ_OK && ret != BZ_STREAM_END) { SETERR(ret); return 0; }
+      if (ret == BZ_OK && at_eof(bzf->handle) && bzf->strm.avail_in == 0 && bzf->strm.avail_out > 0) {
+         SETERR(BZ_UNEXPECTED_EOF); return 0;
+      }
+      if (ret == BZ_STREAM_END) { SETERR(BZ_STREAM_END); return len - (int)bzf->strm.avail_out; }
+      if (bzf->strm.avail_out == 0) { SETERR(BZ_OK); return len; }
+   }
+}
+
+void BZ2_bzReadGetUnused(int* bzerror, BZFILE* b, void** unused, int* nUnused)
+{
+   wfile* bzf = (wfile*)b;
+   if (bzf == NULL) { SETERR(BZ_PARAM_ERROR); return; }
+   if (bzf->last_err != BZ_STREAM_END) { SETERR(BZ_SEQUENCE_ERROR); return; }
+   if (unused == NULL || nUnused == NULL) { SETERR(BZ_PARAM_ERROR); return; }
+   SETERR(BZ_OK);
+   *nUnused = (int)bzf->strm.avail_in;
+   *unused = bzf->strm.next_in;
+}
+
+/* ---- zlib-flavoured convenience layer (bzlib.c:1448-1629) ------------------------------------ */
+static BZFILE* open_common(const char* path, int fd, const char* mode, int by_fd)
+{
+   int err, level = 9, writing = 0, small = 0;
+   FILE* fp;
+   BZFILE* h;
+   if (mode == NULL) return NULL;
+   for (; *mode; mode++) {
+      if (*mode == 'r') writing = 0;
+      else if (*mode == 'w') writing = 1;
+      else if (*mode == 's') small = 1;
+      else if (*mode >= '0' && *mode <= '9') level = *mode - '0';
+   }
+   if (by_fd) fp = fdopen(fd, writing ? "wb" : "rb");
+   else if (path == NULL || path[0] == 0) fp = writing ? stdout : stdin;
+   else fp = fopen(path, writing ? "wb" : "rb");
+   if (fp == NULL) return NULL;
+   if (writing) {
+      if (level < 1) level = 1;
+      if (level > 9) level = 9;
+      h = BZ2_bzWriteOpen(&err, fp, level, 0, 30);
+   } else {
+      h = BZ2_bzReadOpen(&err, fp, 0, small, NULL, 0);
+   }
+   if (h == NULL && fp != stdin && fp != stdout) fclose(fp);
+   return h;
+}
+
+BZFILE* BZ2_bzopen(const char* path, const char* mode) { return open_common(path, -1, mode, 0); }
+BZFILE* BZ2_bzdopen(int fd, const char* mode) { return open_common(NULL, fd, mode, 1); }
+
+int BZ2_bzread(BZFILE* b, void* buf, int len)
+{
+   int err, n;
+   if (((wfile*)b)->last_err == BZ_STREAM_END) return 0;
+   n = BZ2_bzRead(&err, b, buf, len);
+   return (err == BZ_OK || err == BZ_STREAM_END) ? n : -1;
+}
+
+int BZ2_bzwrite(BZFILE* b, void* buf, int len)
+{
+   int err;
+   BZ2_bzWrite(&err, b, buf, len);
+   return err == BZ_OK ? len : -1;
+}
+
+int BZ2_bzflush(BZFILE* b) { (void)b; return 0; }
+
+void BZ2_bzclose(BZFILE* b)
+{
+   int err;
+   FILE* fp;
+   if (b == NULL) return;
+   fp = ((wfile*)b)->handle;
+   if (((wfile*)b)->writing) {
+      BZ2_bzWriteClose(&err, b, 0, NULL, NULL);
+      if (err != BZ_OK) BZ2_bzWriteClose(NULL, b, 1, NULL, NULL);
+   } else {
+      BZ2_bzReadClose(&err, b);
+   }
+   if (fp != stdin && fp != stdout) fclose(fp);
+}
+
+const char* BZ2_bzerror(BZFILE* b, int* errnum)
+{
+   static const char* const names[] = { "OK", "SEQUENCE_ERROR", "PARAM_ERROR", "MEM_ERROR", "DATA_ERROR",
+      "DATA_ERROR_MAGIC", "IO_ERROR", "UNEXPECTED_EOF", "OUTBUFF_FULL", "CONFIG_ERROR" };
+   int err = ((wfile*)b)->last_err;
+   if (err > 0) err = 0;
+   *errnum = err;
+   return (-err < 10) ? names[-err] : "???";
+}

@@ -1,9 +1,9 @@
 /*
  * bzlib.h -- libbz2-compatible public interface of the B200 bzip2 compressor.
  *
- * Drop-in for the compression side of the reference's bzlib.h (aeb1787/bzip2
- * bzlib.h:29-66 constants and bz_stream, :100-128 streaming calls, :204-221
- * one-shot call, :134-199 stdio write calls).  Names, argument meaning, return
+ * Drop-in for the reference's bzlib.h (aeb1787/bzip2 bzlib.h:29-66 constants
+ * and bz_stream, :100-128 streaming calls, :204-221 one-shot calls, :134-199
+ * stdio calls, :238-271 zlib-flavoured calls).  Names, argument meaning, return
  * codes and the bz_stream layout are the reference's, so existing callers
  * relink unchanged; the work behind them runs on the GPU (see bz2_b200.h).
  * Decompression entry points are provided by a small host decoder (used for
@@ -70,6 +70,29 @@ void    BZ2_bzWriteClose64(int* bzerror, BZFILE* b, int abandon,
                            unsigned int* nbytes_out_lo32, unsigned int* nbytes_out_hi32);
 
 const char* BZ2_bzlibVersion(void);
+
+/* streaming and one-shot decompression (reference bzlib.c:488-530, :801-900, :1361-1409).
+ * Host decoder (csrc/bzlib_decode.c); `small` is accepted and ignored. */
+int BZ2_bzDecompressInit(bz_stream* strm, int verbosity, int small);
+int BZ2_bzDecompress(bz_stream* strm);
+int BZ2_bzDecompressEnd(bz_stream* strm);
+int BZ2_bzBuffToBuffDecompress(char* dest, unsigned int* destLen, char* source, unsigned int sourceLen,
+                               int small, int verbosity);
+
+/* stdio read side (reference bzlib.c:1150-1301) */
+BZFILE* BZ2_bzReadOpen(int* bzerror, FILE* f, int verbosity, int small, void* unused, int nUnused);
+void    BZ2_bzReadClose(int* bzerror, BZFILE* b);
+void    BZ2_bzReadGetUnused(int* bzerror, BZFILE* b, void** unused, int* nUnused);
+int     BZ2_bzRead(int* bzerror, BZFILE* b, void* buf, int len);
+
+/* zlib-flavoured layer (reference bzlib.c:1448-1629) */
+BZFILE*     BZ2_bzopen(const char* path, const char* mode);
+BZFILE*     BZ2_bzdopen(int fd, const char* mode);
+int         BZ2_bzread(BZFILE* b, void* buf, int len);
+int         BZ2_bzwrite(BZFILE* b, void* buf, int len);
+int         BZ2_bzflush(BZFILE* b);
+void        BZ2_bzclose(BZFILE* b);
+const char* BZ2_bzerror(BZFILE* b, int* errnum);
 
 #ifdef __cplusplus
 }
