@@ -141,32 +141,36 @@ def sharded_bench(args, torch, dist, B, rank, world, local_rank, dev, data, n, m
         out, info = sh.compress_sharded(be, comm, reg, n, args.level, ends, return_host=not resident)
         return out, info
 
+    # the engine, the NCCL plumbing and the timing events all sit on torch's current stream of this device
+    be.eng.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(resident, steps):
+        """K steps bracketed by barrier + synchronize, timed on the device; returns (max over ranks in s, last result)."""
+        barrier()
+        ev0.record()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            res = one(resident)
+        ev1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        tt = torch.tensor([ev0.elapsed_time(ev1) * 1e-3, wall], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt[0].item()), float(tt[1].item()), res
+
     for _ in range(args.warmup):
         out, info = one(True)
-    barrier()
-    t0 = time.perf_counter()
     with ClockSampler(local_rank) as clk:
-        for _ in range(args.steps):
-            out, info = one(True)
-        barrier()
-    dt = time.perf_counter() - t0
-    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms_per_step = float(tt.item()) / args.steps * 1e3
+        dev_s, wall_s, (out, info) = timed(True, args.steps)
+    ms_per_step = dev_s / args.steps * 1e3
     value = world * n / (ms_per_step * 1e-3) / 1e6
     e2e = None
     if not args.no_e2e:
         for _ in range(max(1, min(args.warmup, 2))):
             host_out, info = one(False)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            host_out, info = one(False)
-        barrier()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": round(world * n * args.steps / float(tt.item()) / 1e6, 2), "unit": "MB/s",
+        e_dev_s, e_wall_s, (host_out, info) = timed(False, args.steps)
+        e2e = {"value": round(world * n * args.steps / max(e_dev_s, e_wall_s) / 1e6, 2), "unit": "MB/s",
                "h2d_bytes_per_step": int(region_h.numel()), "d2h_bytes_per_step": int(info["total_bytes"]) if rank == 0 else 0,
                "api": "bzip2_b200.sharding.compress_sharded over bz2b200_scan_* / bz2b200_compress_device / bz2b200_concat_bits, pinned host buffers"}
         if rank == 0:
@@ -196,7 +200,8 @@ def sharded_bench(args, torch, dist, B, rank, world, local_rank, dev, data, n, m
                 "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config, "clocks": clk.summary(),
                 "e2e": e2e, "gpu_launches": int(st.kernel_launches), "roofline": roof, "cpu_baseline": None,
-                "out_bytes": int(info["total_bytes"]), "blocks_rank0": int(st.n_blocks)}
+                "out_bytes": int(info["total_bytes"]), "blocks_rank0": int(st.n_blocks),
+                "wall_ms_per_step": round(wall_s / args.steps * 1e3, 3)}
         print(json.dumps(line))
     dist.destroy_process_group()
     return 0

@@ -86,6 +86,8 @@ static void engine_free(EngineFull* e)
    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
    for (int i = 0; i < 2; i++) if (e->ev_h2d[i]) cudaEventDestroy(e->ev_h2d[i]);
    for (int i = 0; i < 6; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+   for (int i = 0; i < 3; i++) { if (e->aux[i]) cudaStreamDestroy(e->aux[i]); if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]); }
+   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
    if (e->own_stream) cudaStreamDestroy(e->own_stream);
    free(e);
 }
@@ -112,6 +114,10 @@ static int engine_new(EngineFull** out, int device, int level, size_t window_byt
       e->s2_group = g ? (u32)atoi(g) : 0;
       const char* tf = getenv("BZ2_B200_TEXT_FIRST");
       e->text_first = tf ? (u32)atoi(tf) : 1;
+      const char* kg = getenv("BZ2_B200_KG_MODE");
+      e->kg_mode = kg ? (u32)atoi(kg) : 1;
+      const char* ss = getenv("BZ2_B200_S2_STREAMS");
+      e->s2_streams = ss ? (u32)atoi(ss) : 1;
    }
    if (window_bytes == 0) window_bytes = (size_t)96 << 20;
    // a window must be able to hold the input of one full block of pure runs (255 -> 5 bytes)
@@ -130,12 +136,22 @@ static int engine_new(EngineFull** out, int device, int level, size_t window_byt
       if (c0 != cudaSuccess) { rc = engine_fail(e, c0, __FILE__, __LINE__); goto fail; }
       e->stream = e->own_stream;
       for (int i = 0; i < 6; i++) cudaEventCreate(&e->ev[i]);
+      for (int i = 0; i < 3; i++) {
+         c0 = cudaStreamCreateWithFlags(&e->aux[i], cudaStreamNonBlocking);
+         if (c0 == cudaSuccess) c0 = cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming);
+         if (c0 != cudaSuccess) { rc = engine_fail(e, c0, __FILE__, __LINE__); goto fail; }
+      }
+      c0 = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
+      if (c0 != cudaSuccess) { rc = engine_fail(e, c0, __FILE__, __LINE__); goto fail; }
       ALLOC(e->enc, E + 64); ALLOC(e->cend, E + 64);
       ALLOC(e->sa, E + 64); ALLOC(e->rank, E + 64);
       ALLOC(e->keyA, E + 64); ALLOC(e->keyB, E + 64); ALLOC(e->idxB, E + 64);
       ALLOC(e->bwt, E + 64); ALLOC(e->z, E + 64); ALLOC(e->mtfv, E + B + 64);
+      u32 hist_log2 = 18;
+      { const char* hl = getenv("BZ2_B200_HIST_LOG2"); if (hl) { const int v = atoi(hl); if (v >= 16 && v <= 22) hist_log2 = (u32)v; } }
       e->hist_stride = 1u << 16;
-      while (e->hist_stride < (1u << 18) && e->hist_stride < e->nmax / 4) e->hist_stride <<= 1;
+      while (e->hist_stride < (1u << hist_log2) && e->hist_stride < e->nmax / 4) e->hist_stride <<= 1;
+      if (hist_log2 > 18 && e->hist_stride < e->nmax * 2u) e->hist_stride = 1u << hist_log2;
       ALLOC(e->hist, B * e->hist_stride);
       ALLOC(e->code, B * 256); ALLOC(e->kk, B); ALLOC(e->nbins, B); ALLOC(e->hh, B); ALLOC(e->kbits, B); ALLOC(e->ksym, B);
       ALLOC(e->K, E + 64); ALLOC(e->kscrA, E + 64); ALLOC(e->kscrB, E + 64);

@@ -110,6 +110,10 @@ struct Engine {
    u32 *kk, *nbins, *hh, *kbits, *ksym;   // [blk_cap]
    u64 *K, *kscrA, *kscrB; // [E] packed text keys; 64-bit key scratch of the large path
    u32 text_first;         // first refinement round sorts by text keys (default on)
+   u32 kg_mode;            // k-gram bucket sort: 0 = count / rank / atomic scatter, 1 = count with arrival index / place
+   u32 s2_streams;         // run the size classes of a refinement round on side streams (default on)
+   cudaStream_t aux[3];    // side streams of the BWT rounds
+   cudaEvent_t ev_fork, ev_join[3];
    u32 *blockmap;          // [enc_cap/4096 + 2] block id of each 4 KiB chunk of enc
    SegLists lists;
    BlockTables bt;

@@ -205,7 +205,9 @@ __global__ void __launch_bounds__(S1_THREADS) k_tile(S1Params p)
          if (wr) p.enc[E] = (u8)ch;
          if (last) { if (wr) p.enc[E + 1] = 0; p.cend[E + 1] = 1; }
          E += 2;
-      } else {
+      } else if (E > 0) {
+         // E == 0 only in a shard scan that starts inside a run past its fourth byte: that chunk's count
+         // byte belongs to the previous shard's encoding, and no block can start before offset 0 here
          if (last) { if (wr) p.enc[E - 1] = (u8)(jj - 3); p.cend[E - 1] = 1; }
       }
    }
@@ -474,16 +476,21 @@ int scan_build(ScanState* s, u32 prev_byte, u32 carry0)
    p.tile_size = s->tile_size; p.tile_base = s->tile_base;
    p.enc = nullptr; p.cend = s->cend; p.scalars = s->scal;
    p.prev_byte = prev_byte; p.carry0 = carry0;
-   k_tile<S1_AGG><<<s->ntiles, S1_THREADS, 0, st>>>(p);
-   k_scan_runs<<<1, 1024, 0, st>>>(s->tile_len, s->tile_ext, s->tile_carry, s->ntiles, carry0);
-   k_tile<S1_COUNT><<<s->ntiles, S1_THREADS, 0, st>>>(p);
-   k_scan_u32<<<1, 1024, 0, st>>>(s->tile_size, s->tile_base, s->ntiles, s->scal + 2);
+   const bool dbg = getenv("BZ2_B200_DEBUG_SYNC") != nullptr;
+#define SCAN_DBG(name) do { if (dbg) { cudaError_t c_ = cudaStreamSynchronize(st); if (c_ == cudaSuccess) c_ = cudaGetLastError(); \
+      if (c_ != cudaSuccess) { fprintf(stderr, "[bz2b200] scan %s: %s\n", name, cudaGetErrorString(c_)); return -1; } } } while (0)
+   SCAN_DBG("entry");
+   k_tile<S1_AGG><<<s->ntiles, S1_THREADS, 0, st>>>(p);                                           SCAN_DBG("k_tile<AGG>");
+   k_scan_runs<<<1, 1024, 0, st>>>(s->tile_len, s->tile_ext, s->tile_carry, s->ntiles, carry0);   SCAN_DBG("k_scan_runs");
+   k_tile<S1_COUNT><<<s->ntiles, S1_THREADS, 0, st>>>(p);                                         SCAN_DBG("k_tile<COUNT>");
+   k_scan_u32<<<1, 1024, 0, st>>>(s->tile_size, s->tile_base, s->ntiles, s->scal + 2);           SCAN_DBG("k_scan_u32");
    if (cudaMemcpyAsync(s->h_scal, s->scal, 4 * sizeof(u32), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
    if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
    s->enc_total = s->h_scal[2];
    if ((u64)s->enc_total + 16 > s->cend_cap) return -2;
    if (cudaMemsetAsync(s->cend, 0, (size_t)s->enc_total + 16, st) != cudaSuccess) return -1;
-   k_tile<S1_SCATTER><<<s->ntiles, S1_THREADS, 0, st>>>(p);
+   k_tile<S1_SCATTER><<<s->ntiles, S1_THREADS, 0, st>>>(p);                                       SCAN_DBG("k_tile<SCATTER>");
+#undef SCAN_DBG
    if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
    return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

@@ -125,7 +125,7 @@ constexpr int KG_ITEMS = 16;
 constexpr int KG_TILE = KG_THREADS * KG_ITEMS;
 constexpr int KG_MAXK = 24;
 
-enum { KG_HIST = 0, KG_RANK = 1, KG_SCATTER = 2 };
+enum { KG_HIST = 0, KG_RANK = 1, KG_SCATTER = 2, KG_HISTOFF = 3, KG_PLACE = 4 };
 
 __global__ void __launch_bounds__(KG_THREADS) k_inuse(S2Params p)
 {
@@ -189,7 +189,8 @@ __global__ void __launch_bounds__(KG_THREADS) k_kgram(S2Params p)
    cmap[threadIdx.x] = p.code[(size_t)b * 256 + threadIdx.x];
    __syncthreads();
    const u32 msym = p.ksym[b] & 255u, mbits = p.ksym[b] >> 8;
-   const u32 halo = (MODE == KG_RANK && p.text_first) ? max(k, msym) : k;
+   const u32 halo = ((MODE == KG_RANK || MODE == KG_PLACE) && p.text_first) ? max(k, msym) : k;
+   u32* const koff = reinterpret_cast<u32*>(p.kscrA);
    const u32 span = min((u32)KG_TILE, n - t0) + halo - 1;
    for (u32 s = threadIdx.x; s < span; s += KG_THREADS) {
       u32 gi = t0 + s;
@@ -205,8 +206,11 @@ __global__ void __launch_bounds__(KG_THREADS) k_kgram(S2Params p)
          u32 key = 0;
          for (u32 j = 0; j < k; j++) key = key * base + sc[s + j];
          if (MODE == KG_HIST) atomicAdd(&hist[key], 1u);
-         else if (MODE == KG_RANK) {
-            p.rank[xb + i] = rk_pack(0xffffu, 0, hist[key]);
+         else if (MODE == KG_HISTOFF) koff[xb + i] = atomicAdd(&hist[key], 1u);     // arrival order inside the bucket
+         else if (MODE == KG_RANK || MODE == KG_PLACE) {
+            const u32 start = hist[key];
+            p.rank[xb + i] = rk_pack(0xffffu, 0, start);
+            if (MODE == KG_PLACE) p.sa[xb + start + koff[xb + i]] = i;
             if (p.text_first) {
                u64 kw = 0;
                for (u32 j = 0; j < msym; j++) kw = (kw << mbits) | (u64)sc[s + j];
@@ -252,6 +256,7 @@ __global__ void __launch_bounds__(1024) k_kgram_scan(S2Params p)
 }
 
 // after the scatter hist[bin] is the END of bucket `bin`; emit the initial segments
+template <bool ENDS>
 __global__ void __launch_bounds__(256) k_seg_init(S2Params p, ListsDev L)
 {
    const u32 b = p.b0 + blockIdx.y;
@@ -259,8 +264,9 @@ __global__ void __launch_bounds__(256) k_seg_init(S2Params p, ListsDev L)
    const u32* hist = p.hist + (size_t)(b - p.b0) * p.hist_stride;
    const u32 bin = blockIdx.x * 256 + threadIdx.x;
    const bool vbin = bin < p.nbins[b];
-   const u32 end = vbin ? hist[bin] : 0;
-   const u32 start = (vbin && bin) ? hist[bin - 1] : 0;
+   // ENDS: the scatter pass left hist[bin] = end of the bucket; otherwise hist[bin] is still its start
+   const u32 end = !vbin ? 0 : ENDS ? hist[bin] : (bin + 1 < p.nbins[b] ? hist[bin + 1] : n);
+   const u32 start = !vbin ? 0 : ENDS ? (bin ? hist[bin - 1] : 0) : hist[bin];
    const u32 len = end - start;
    const bool multi = vbin && len >= 2;
    const bool deep = (p.kk[b] >= n);                  // depth k already covers the whole rotation
@@ -693,34 +699,41 @@ static ListsDev lists_dev(Engine* e, int which)
    return L;
 }
 
+static bool trace_on()
+{
+   static int on = -1;
+   if (on < 0) { const char* v = getenv("BZ2_B200_TRACE"); on = (v && *v >= '1') ? 1 : 0; }
+   return on == 1;
+}
+
 // BZ2_B200_DEBUG_SYNC=1: synchronise after every refinement launch and name the kernel that faulted
 static bool dbg_sync(Engine* e, const char* what)
 {
    static int on = -1;
    if (on < 0) { const char* v = getenv("BZ2_B200_DEBUG_SYNC"); on = (v && *v >= '1') ? 1 : 0; }
    if (!on) return true;
-   cudaError_t c = cudaStreamSynchronize(e->stream);
+   cudaError_t c = cudaDeviceSynchronize();
    if (c == cudaSuccess) c = cudaGetLastError();
    if (c != cudaSuccess) { fprintf(stderr, "[bz2b200] %s: %s\n", what, cudaGetErrorString(c)); return false; }
    return true;
 }
 
 template <int LANES>
-static void launch_small(Engine* e, const S2Params& p, const ListsDev& Lout, const u32* items, u32 count, u32 round, bool text)
+static void launch_small(Engine* e, cudaStream_t st, const S2Params& p, const ListsDev& Lout, const u32* items, u32 count, u32 round, bool text)
 {
    const u64 threads = (u64)count * LANES;
    const u32 grid = (u32)((threads + 255) / 256);
-   if (text) k_refine_small<LANES, true><<<grid, 256, 0, e->stream>>>(p, Lout, items, count, round);
-   else      k_refine_small<LANES, false><<<grid, 256, 0, e->stream>>>(p, Lout, items, count, round);
+   if (text) k_refine_small<LANES, true><<<grid, 256, 0, st>>>(p, Lout, items, count, round);
+   else      k_refine_small<LANES, false><<<grid, 256, 0, st>>>(p, Lout, items, count, round);
    char nm[64]; snprintf(nm, sizeof nm, "k_refine_small<%d,%d> count=%u round=%u", LANES, (int)text, count, round); dbg_sync(e, nm);
 }
 template <int THREADS>
-static void launch_medium(Engine* e, const S2Params& p, const ListsDev& Lout, const u64* items, u32 count, u32 round, bool text)
+static void launch_medium(Engine* e, cudaStream_t st, const S2Params& p, const ListsDev& Lout, const u64* items, u32 count, u32 round, bool text)
 {
    const u32 grid = (THREADS == 32) ? (count + 7) / 8 : count;
    const u32 block = (THREADS == 32) ? 256 : THREADS;
-   if (text) k_refine_medium<THREADS, true><<<grid, block, 0, e->stream>>>(p, Lout, items, count, round);
-   else      k_refine_medium<THREADS, false><<<grid, block, 0, e->stream>>>(p, Lout, items, count, round);
+   if (text) k_refine_medium<THREADS, true><<<grid, block, 0, st>>>(p, Lout, items, count, round);
+   else      k_refine_medium<THREADS, false><<<grid, block, 0, st>>>(p, Lout, items, count, round);
    char nm[64]; snprintf(nm, sizeof nm, "k_refine_medium<%d,%d> count=%u round=%u", THREADS, (int)text, count, round); dbg_sync(e, nm);
 }
 
@@ -754,11 +767,20 @@ int stage2_run(Engine* e, u32 nb, u32 E)
       const dim3 gtiles((max_n + KG_TILE - 1) / KG_TILE, g);
       k_inuse<<<gtiles, KG_THREADS, 0, st>>>(p);                                                BZ_KCHECK(e);
       k_codemap<<<g, 256, 0, st>>>(p);                                                          BZ_KCHECK(e);
-      k_kgram<KG_HIST><<<gtiles, KG_THREADS, 0, st>>>(p);                                       BZ_KCHECK(e);
-      k_kgram_scan<<<g, 1024, 0, st>>>(p);                                                      BZ_KCHECK(e);
-      k_kgram<KG_RANK><<<gtiles, KG_THREADS, 0, st>>>(p);                                       BZ_KCHECK(e);
-      k_kgram<KG_SCATTER><<<gtiles, KG_THREADS, 0, st>>>(p);                                    BZ_KCHECK(e);
-      k_seg_init<<<dim3((e->hist_stride + 255) / 256, g), 256, 0, st>>>(p, lists_dev(e, 0));    BZ_KCHECK(e);
+      if (e->kg_mode == 0) {
+         k_kgram<KG_HIST><<<gtiles, KG_THREADS, 0, st>>>(p);                                       BZ_KCHECK(e);
+         k_kgram_scan<<<g, 1024, 0, st>>>(p);                                                      BZ_KCHECK(e);
+         k_kgram<KG_RANK><<<gtiles, KG_THREADS, 0, st>>>(p);                                       BZ_KCHECK(e);
+         k_kgram<KG_SCATTER><<<gtiles, KG_THREADS, 0, st>>>(p);                                    BZ_KCHECK(e);
+         k_seg_init<true><<<dim3((e->hist_stride + 255) / 256, g), 256, 0, st>>>(p, lists_dev(e, 0)); BZ_KCHECK(e);
+      } else {
+         // one atomic pass: the count pass keeps each rotation's arrival index inside its bucket, so the
+         // placement pass needs no atomics (bucket start + arrival index)
+         k_kgram<KG_HISTOFF><<<gtiles, KG_THREADS, 0, st>>>(p);                                    BZ_KCHECK(e);
+         k_kgram_scan<<<g, 1024, 0, st>>>(p);                                                      BZ_KCHECK(e);
+         k_kgram<KG_PLACE><<<gtiles, KG_THREADS, 0, st>>>(p);                                      BZ_KCHECK(e);
+         k_seg_init<false><<<dim3((e->hist_stride + 255) / 256, g), 256, 0, st>>>(p, lists_dev(e, 0)); BZ_KCHECK(e);
+      }
       dbg_sync(e, "k-gram phase");
 
       int cur = 0;
@@ -770,6 +792,26 @@ int stage2_run(Engine* e, u32 nb, u32 E)
          u32 cnt[N_CLASSES]; u64 total = 0;
          for (int c = 0; c < N_CLASSES; c++) { cnt[c] = e->h_counts[c]; total += cnt[c]; }
          if (total == 0) break;
+         if (trace_on()) {
+            // BZ2_B200_TRACE=1: segments and elements per size class, every round (debug only: copies the lists)
+            fprintf(stderr, "[bz2b200] round %u:", round);
+            for (int c = 0; c < N_CLASSES; c++) {
+               u64 elems = 0;
+               if (cnt[c] && c >= N_SMALL_CLASSES) {
+                  u64* h = (u64*)malloc(sizeof(u64) * cnt[c]);
+                  cudaMemcpy(h, e->lists.big_items[cur][c - N_SMALL_CLASSES], sizeof(u64) * cnt[c], cudaMemcpyDeviceToHost);
+                  for (u32 i = 0; i < cnt[c]; i++) elems += h[i] & 0xfffffu;
+                  free(h);
+               } else if (cnt[c]) {
+                  u32* h = (u32*)malloc(sizeof(u32) * cnt[c]);
+                  cudaMemcpy(h, e->lists.small_items[cur][c], sizeof(u32) * cnt[c], cudaMemcpyDeviceToHost);
+                  for (u32 i = 0; i < cnt[c]; i++) elems += (h[i] >> 27) + 1;
+                  free(h);
+               }
+               fprintf(stderr, " c%d=%u/%llu", c, cnt[c], (unsigned long long)elems);
+            }
+            fprintf(stderr, "\n");
+         }
          if (round > 22) { snprintf(e->err, sizeof e->err, "prefix doubling did not terminate"); return -5; }
          const int nxt = cur ^ 1;
          BZ_CUDA(e, cudaMemsetAsync(e->lists.counts[nxt], 0, sizeof(u32) * N_CLASSES, st));
@@ -777,21 +819,36 @@ int stage2_run(Engine* e, u32 nb, u32 E)
          u32** si = e->lists.small_items[cur];
          u64** bi = e->lists.big_items[cur];
          const bool text = (round == 0) && e->text_first;
+         // The size classes of one round touch disjoint segments, so they run side by side: the few
+         // long-running CTAs of the large and CTA-sort classes overlap the sub-warp classes' tails.
+         const bool fork = e->s2_streams && total > 64;
+         cudaStream_t sL = st, sM = st, sW = st;
+         if (fork) {
+            sL = e->aux[0]; sM = e->aux[1]; sW = e->aux[2];
+            BZ_CUDA(e, cudaEventRecord(e->ev_fork, st));
+            for (int a = 0; a < 3; a++) BZ_CUDA(e, cudaStreamWaitEvent(e->aux[a], e->ev_fork, 0));
+         }
          if (cnt[CLS_LARGE]) {
-            if (text) k_refine_large<true><<<cnt[CLS_LARGE], LG_THREADS, 0, st>>>(p, Lout, bi[5], round);
-            else      k_refine_large<false><<<cnt[CLS_LARGE], LG_THREADS, 0, st>>>(p, Lout, bi[5], round);
+            if (text) k_refine_large<true><<<cnt[CLS_LARGE], LG_THREADS, 0, sL>>>(p, Lout, bi[5], round);
+            else      k_refine_large<false><<<cnt[CLS_LARGE], LG_THREADS, 0, sL>>>(p, Lout, bi[5], round);
             dbg_sync(e, "k_refine_large");
          }
-         if (cnt[CLS_C4K])   launch_medium<512>(e, p, Lout, bi[4], cnt[CLS_C4K], round, text);
-         if (cnt[CLS_C2K])   launch_medium<256>(e, p, Lout, bi[3], cnt[CLS_C2K], round, text);
-         if (cnt[CLS_C1K])   launch_medium<128>(e, p, Lout, bi[2], cnt[CLS_C1K], round, text);
-         if (cnt[CLS_C512])  launch_medium<64>(e, p, Lout, bi[1], cnt[CLS_C512], round, text);
-         if (cnt[CLS_W256])  launch_medium<32>(e, p, Lout, bi[0], cnt[CLS_W256], round, text);
-         if (cnt[4]) launch_small<32>(e, p, Lout, si[4], cnt[4], round, text);
-         if (cnt[3]) launch_small<16>(e, p, Lout, si[3], cnt[3], round, text);
-         if (cnt[2]) launch_small<8>(e, p, Lout, si[2], cnt[2], round, text);
-         if (cnt[1]) launch_small<4>(e, p, Lout, si[1], cnt[1], round, text);
-         if (cnt[0]) launch_small<2>(e, p, Lout, si[0], cnt[0], round, text);
+         if (cnt[CLS_C4K])   launch_medium<512>(e, sM, p, Lout, bi[4], cnt[CLS_C4K], round, text);
+         if (cnt[CLS_C2K])   launch_medium<256>(e, sM, p, Lout, bi[3], cnt[CLS_C2K], round, text);
+         if (cnt[CLS_C1K])   launch_medium<128>(e, sW, p, Lout, bi[2], cnt[CLS_C1K], round, text);
+         if (cnt[CLS_C512])  launch_medium<64>(e, sW, p, Lout, bi[1], cnt[CLS_C512], round, text);
+         if (cnt[CLS_W256])  launch_medium<32>(e, sW, p, Lout, bi[0], cnt[CLS_W256], round, text);
+         if (cnt[4]) launch_small<32>(e, st, p, Lout, si[4], cnt[4], round, text);
+         if (cnt[3]) launch_small<16>(e, st, p, Lout, si[3], cnt[3], round, text);
+         if (cnt[2]) launch_small<8>(e, st, p, Lout, si[2], cnt[2], round, text);
+         if (cnt[1]) launch_small<4>(e, st, p, Lout, si[1], cnt[1], round, text);
+         if (cnt[0]) launch_small<2>(e, st, p, Lout, si[0], cnt[0], round, text);
+         if (fork) {
+            for (int a = 0; a < 3; a++) {
+               BZ_CUDA(e, cudaEventRecord(e->ev_join[a], e->aux[a]));
+               BZ_CUDA(e, cudaStreamWaitEvent(st, e->ev_join[a], 0));
+            }
+         }
          u32 nl = 0;
          for (int c = 0; c < N_CLASSES; c++) nl += cnt[c] ? 1u : 0u;
          e->launches += nl - 1;
