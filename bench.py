@@ -52,15 +52,51 @@ def make_input(workload, n, rank=0):
 
 
 class ClockSampler:
-    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line), through
+    NVML in-process and at a rate that adapts to what a query costs: a query takes the driver's lock, and on some
+    boxes spawning nvidia-smi (or polling NVML every few ms) stretched the timed step by 10 % to 4x."""
 
-    def __init__(self, index):
+    def __init__(self, index, count=1):
         self.rows = []
         self.stop = False
         self.index = index
+        self.count = count            # GPUs index .. index+count-1 are sampled (rank 0 samples every local GPU)
+        self.how = "nvml"
+        self.query_ms = []
         self.th = threading.Thread(target=self.run, daemon=True)
 
-    def run(self):
+    def _run_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        hs = []
+        for k in range(self.index, self.index + self.count):
+            idx = k
+            if vis:
+                try:
+                    idx = int(vis.split(",")[k])
+                except Exception:  # noqa: BLE001
+                    pass
+            hs.append(nv.nvmlDeviceGetHandleByIndex(idx))
+        mx = [nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM) for h in hs]
+        bits = [(nv.nvmlClocksEventReasonHwSlowdown, 0), (nv.nvmlClocksEventReasonHwThermalSlowdown, 1),
+                (nv.nvmlClocksEventReasonSwThermalSlowdown, 2), (nv.nvmlClocksEventReasonSwPowerCap, 3)]
+        self.ready.set()
+        while not self.stop:
+            t0 = time.perf_counter()
+            for h, m in zip(hs, mx):
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                row = [str(sm), str(m)] + ["Not Active"] * 4
+                for bit, k in bits:
+                    if r & bit:
+                        row[2 + k] = "Active"
+                self.rows.append(row)
+            dt = time.perf_counter() - t0
+            self.query_ms.append(dt * 1e3)
+            time.sleep(max(0.1, 30.0 * dt))     # keep the sampler under ~3 % of the wall clock
+
+    def _run_smi(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self.stop:
@@ -71,10 +107,20 @@ class ClockSampler:
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.2)
+            time.sleep(1.0)
+
+    def run(self):
+        try:
+            self._run_nvml()
+        except Exception:  # noqa: BLE001
+            self.how = "nvidia-smi"
+            self.ready.set()
+            self._run_smi()
 
     def __enter__(self):
+        self.ready = threading.Event()
         self.th.start()
+        self.ready.wait(timeout=10)          # NVML initialisation stays outside the timed region
         return self
 
     def __exit__(self, *a):
@@ -88,7 +134,8 @@ class ClockSampler:
         mx = max(int(r[1]) for r in self.rows if r[1].isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for k, n in enumerate(names) if any(r[2 + k].lower().startswith("active") for r in self.rows if len(r) > 2 + k)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.rows)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.rows),
+                "source": self.how, "query_ms": round(sorted(self.query_ms)[len(self.query_ms) // 2], 3) if self.query_ms else None}
 
 
 def cpu_reference_rate(data, level, threads, seconds_budget, sample_bytes):
@@ -136,22 +183,36 @@ def sharded_bench(args, torch, dist, B, rank, world, local_rank, dev, data, n, m
         dist.barrier()
         torch.cuda.synchronize()
 
+    h2d_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+
     def one(resident):
-        reg = region_d if resident else region_h.to(dev, non_blocking=True)
+        if resident:
+            reg = region_d
+        else:
+            h2d_ev[0].record()
+            reg = region_h.to(dev, non_blocking=True)
+            h2d_ev[1].record()
         out, info = sh.compress_sharded(be, comm, reg, n, args.level, ends, return_host=not resident)
+        if not resident:
+            info["protocol_ms"]["h2d_copy"] = round(h2d_ev[0].elapsed_time(h2d_ev[1]), 3)
         return out, info
 
     # the engine, the NCCL plumbing and the timing events all sit on torch's current stream of this device
     be.eng.set_stream(torch.cuda.current_stream(dev).cuda_stream)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
+    per_step = []          # this rank's host-side time of every timed step (diagnostic)
+
     def timed(resident, steps):
         """K steps bracketed by barrier + synchronize, timed on the device; returns (max over ranks in s, last result)."""
         barrier()
         ev0.record()
         t0 = time.perf_counter()
+        per_step.clear()
         for _ in range(steps):
+            t1 = time.perf_counter()
             res = one(resident)
+            per_step.append(round((time.perf_counter() - t1) * 1e3, 2))
         ev1.record()
         barrier()
         wall = time.perf_counter() - t0
@@ -161,16 +222,23 @@ def sharded_bench(args, torch, dist, B, rank, world, local_rank, dev, data, n, m
 
     for _ in range(args.warmup):
         out, info = one(True)
-    with ClockSampler(local_rank) as clk:
+    import contextlib
+    # rank 0 samples every GPU of the node; one sampler per rank only multiplies the driver-lock traffic
+    with (ClockSampler(0, world) if rank == 0 else contextlib.nullcontext()) as clk:
         dev_s, wall_s, (out, info) = timed(True, args.steps)
     ms_per_step = dev_s / args.steps * 1e3
+    resident_steps = list(per_step)
+    proto = [None] * world
+    dist.all_gather_object(proto, info.get("protocol_ms"))
     value = world * n / (ms_per_step * 1e-3) / 1e6
     e2e = None
     if not args.no_e2e:
         for _ in range(max(1, min(args.warmup, 2))):
             host_out, info = one(False)
         e_dev_s, e_wall_s, (host_out, info) = timed(False, args.steps)
-        e2e = {"value": round(world * n * args.steps / max(e_dev_s, e_wall_s) / 1e6, 2), "unit": "MB/s",
+        e_proto = [None] * world
+        dist.all_gather_object(e_proto, info.get("protocol_ms"))
+        e2e = {"value": round(world * n * args.steps / max(e_dev_s, e_wall_s) / 1e6, 2), "unit": "MB/s", "protocol_ms_per_rank": e_proto, "step_ms_rank0": list(per_step),
                "h2d_bytes_per_step": int(region_h.numel()), "d2h_bytes_per_step": int(info["total_bytes"]) if rank == 0 else 0,
                "api": "bzip2_b200.sharding.compress_sharded over bz2b200_scan_* / bz2b200_compress_device / bz2b200_concat_bits, pinned host buffers"}
         if rank == 0:
@@ -201,7 +269,7 @@ def sharded_bench(args, torch, dist, B, rank, world, local_rank, dev, data, n, m
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config, "clocks": clk.summary(),
                 "e2e": e2e, "gpu_launches": int(st.kernel_launches), "roofline": roof, "cpu_baseline": None,
                 "out_bytes": int(info["total_bytes"]), "blocks_rank0": int(st.n_blocks),
-                "wall_ms_per_step": round(wall_s / args.steps * 1e3, 3)}
+                "wall_ms_per_step": round(wall_s / args.steps * 1e3, 3), "protocol_ms_per_rank": proto, "step_ms_rank0": resident_steps}
         print(json.dumps(line))
     dist.destroy_process_group()
     return 0

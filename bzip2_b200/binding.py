@@ -44,7 +44,7 @@ EXPORTS = [
     "bz2b200_device_count", "bz2b200_last_error", "bz2b200_version", "bz2b200_engine_create",
     "bz2b200_engine_destroy", "bz2b200_engine_set_stream", "bz2b200_compress_host", "bz2b200_compress_device", "bz2b200_stream_begin",
     "bz2b200_stream_feed", "bz2b200_debug_keep", "bz2b200_debug_fetch",
-    "bz2b200_scan_create", "bz2b200_scan_boundary", "bz2b200_scan_destroy", "bz2b200_concat_bits",
+    "bz2b200_scan_create", "bz2b200_scan_rescan", "bz2b200_scan_boundary", "bz2b200_scan_destroy", "bz2b200_concat_bits",
     # include/bzlib.h
     "BZ2_bzCompressInit", "BZ2_bzCompress", "BZ2_bzCompressEnd", "BZ2_bzBuffToBuffCompress",
     "BZ2_bzWriteOpen", "BZ2_bzWrite", "BZ2_bzWriteClose", "BZ2_bzWriteClose64", "BZ2_bzlibVersion",
@@ -81,6 +81,8 @@ def load():
     lib.bz2b200_debug_fetch.argtypes = [vp, C.c_char_p, vp, sz, C.POINTER(sz)]
     lib.bz2b200_scan_create.restype = C.c_int
     lib.bz2b200_scan_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, vp, sz, C.c_int, C.c_uint64, C.c_int]
+    lib.bz2b200_scan_rescan.restype = C.c_int
+    lib.bz2b200_scan_rescan.argtypes = [vp, vp, sz, C.c_int, C.c_uint64, C.c_int]
     lib.bz2b200_scan_boundary.restype = C.c_int
     lib.bz2b200_scan_boundary.argtypes = [vp, sz, sz, C.c_uint, C.POINTER(sz), C.POINTER(C.c_uint32)]
     lib.bz2b200_scan_destroy.restype = None

@@ -568,7 +568,7 @@ int bz2b200_engine_set_stream(bz2b200_engine* h, void* cuda_stream)
    return 0;
 }
 
-struct bz2b200_scan { ScanState s; };
+struct bz2b200_scan { ScanState s; size_t cap; };
 
 void bz2b200_scan_destroy(bz2b200_scan* h)
 {
@@ -582,6 +582,13 @@ void bz2b200_scan_destroy(bz2b200_scan* h)
    free(h);
 }
 
+static void scan_set_input(ScanState& s, const void* d_src, size_t n, int prev_byte, uint64_t prev_run, int input_ends)
+{
+   s.in = static_cast<const u8*>(d_src); s.W = (u32)n; s.input_ends = input_ends ? 1u : 0u;
+   s.prev_byte = (prev_byte >= 0 && prev_byte < 256 && prev_run) ? (u32)prev_byte : 256u;
+   s.carry0 = (s.prev_byte < 256) ? (u32)(prev_run % 255u) : 0u;
+}
+
 int bz2b200_scan_create(bz2b200_scan** out, int device, int level, const void* d_src, size_t n,
                         int prev_byte, uint64_t prev_run, int input_ends)
 {
@@ -593,10 +600,9 @@ int bz2b200_scan_create(bz2b200_scan** out, int device, int level, const void* d
    ScanState& s = h->s;
    DeviceGuard guard(device);
    s.device = device; s.nmax = 100000u * (u32)level - 19u;
-   s.in = static_cast<const u8*>(d_src); s.W = (u32)n; s.input_ends = input_ends ? 1u : 0u;
-   s.prev_byte = (prev_byte >= 0 && prev_byte < 256 && prev_run) ? (u32)prev_byte : 256u;
-   s.carry0 = (s.prev_byte < 256) ? (u32)(prev_run % 255u) : 0u;
+   scan_set_input(s, d_src, n, prev_byte, prev_run, input_ends);
    const size_t nt = n / 4096 + 4;
+   h->cap = n;
    s.cend_cap = n + n / 4 + 4096;
    bool ok = cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) == cudaSuccess;
    ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.tile_len), nt * 4) == cudaSuccess;
@@ -613,6 +619,19 @@ int bz2b200_scan_create(bz2b200_scan** out, int device, int level, const void* d
    const int rc = n ? scan_build(&s, s.prev_byte, s.carry0) : 0;
    if (rc) { bz2b200_scan_destroy(h); return set_err(BZ2B200_ECUDA, "shard scan failed"); }
    *out = h;
+   return 0;
+}
+
+int bz2b200_scan_rescan(bz2b200_scan* h, const void* d_src, size_t n, int prev_byte, uint64_t prev_run, int input_ends)
+{
+   if (!h || (!d_src && n)) return set_err(BZ2B200_EPARAM, "bad argument");
+   if (n > h->cap) return set_err(BZ2B200_EOUTFULL, "region larger than the scan was created for");
+   ScanState& s = h->s;
+   DeviceGuard guard(s.device);
+   scan_set_input(s, d_src, n, prev_byte, prev_run, input_ends);
+   cudaMemsetAsync(s.scal, 0, 16 * 4, s.st);
+   const int rc = n ? scan_build(&s, s.prev_byte, s.carry0) : 0;
+   if (rc) return set_err(BZ2B200_ECUDA, "shard scan failed");
    return 0;
 }
 

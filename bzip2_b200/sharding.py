@@ -157,11 +157,23 @@ class GpuBackend:
         return t.to(self.dev, non_blocking=False)
 
     def scan(self, region, prev_byte, prev_run, input_ends):
+        # the scan's buffers are kept between calls (a step loop pays no cudaMalloc / cudaFree)
+        n = region.numel()
+        h = getattr(self, "_scan", None)
+        if h is not None and n <= self._scan_cap:
+            rc = self.lib.bz2b200_scan_rescan(h, region.data_ptr(), n, prev_byte, prev_run, 1 if input_ends else 0)
+            if rc:
+                raise self.binding.Bz2B200Error(f"scan_rescan rc={rc}: {self.lib.bz2b200_last_error().decode()}")
+            return h
+        if h is not None:
+            self.lib.bz2b200_scan_destroy(h)
+            self._scan = None
         h = C.c_void_p()
-        rc = self.lib.bz2b200_scan_create(C.byref(h), self.device, self.level, region.data_ptr(), region.numel(),
+        rc = self.lib.bz2b200_scan_create(C.byref(h), self.device, self.level, region.data_ptr(), n,
                                           prev_byte, prev_run, 1 if input_ends else 0)
         if rc:
             raise self.binding.Bz2B200Error(f"scan_create rc={rc}: {self.lib.bz2b200_last_error().decode()}")
+        self._scan, self._scan_cap = h, n
         return h
 
     def boundary(self, scan, start, limit, tail_streamed):
@@ -172,7 +184,18 @@ class GpuBackend:
         return int(b.value), int(nb.value)
 
     def free_scan(self, scan):
-        self.lib.bz2b200_scan_destroy(scan)
+        pass                                   # kept for the next call; released by close()
+
+    def close(self):
+        if getattr(self, "_scan", None) is not None:
+            self.lib.bz2b200_scan_destroy(self._scan)
+            self._scan = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
 
     def compress_segment(self, region, start, end, flags):
         n = end - start
@@ -221,14 +244,19 @@ def compress_sharded(backend, comm, region, shard_len, level, stream_ends_in_reg
           send_piece(dst, piece, nbytes), recv_piece(src, nbytes) -> piece.
     Returns the finished stream (bytes) on rank 0 (None elsewhere) and a dict of counters.
     """
+    import time as _time
     rank, world = comm.rank, comm.world
+    marks = [("start", _time.perf_counter())]
+    mark = lambda name: marks.append((name, _time.perf_counter()))
     n_region = int(region.numel() if hasattr(region, "numel") else region.size)
     host_view = comm.host_view(region, shard_len)
     infos = comm.all_gather_ints(list(run_info(host_view)))
+    mark("run_info")
     prev_byte, prev_run = prev_state(infos, rank)
     lens = [i[5] for i in infos]
     base = sum(lens[:rank])                              # global offset of this shard
     scan = backend.scan(region, prev_byte, prev_run, stream_ends_in_region) if shard_len else None
+    mark("scan")
     # 2. the chain: global offset of my first block boundary
     start_g = 0 if rank == 0 else comm.recv_int(rank - 1)
     last = rank == world - 1
@@ -243,21 +271,30 @@ def compress_sharded(backend, comm, region, shard_len, level, stream_ends_in_reg
         next_g = base + b_loc
     if not last:
         comm.send_int(rank + 1, next_g)
+    mark("chain")
     if scan is not None and hasattr(backend, "free_scan"):
         backend.free_scan(scan)
     # 3. my piece
     flags = NO_HEADER | NO_TRAILER | (TAIL_STREAMED if tail_streamed else 0)
     piece, nbits, nblk, fold = backend.compress_segment(region, seg[0], seg[1], flags)
+    mark("compress")
     # 4. assembly on rank 0
     meta = comm.all_gather_ints([nbits, nblk, fold])
+    mark("meta")
     offs = [32]
     for m in meta:
         offs.append(offs[-1] + m[0])
     total_bits = offs[-1] + 80
     nbytes = (total_bits + 7) // 8
     info = {"segment": (base + seg[0], base + seg[1]), "nbits": nbits, "blocks": nblk, "total_bytes": nbytes}
+
+    def finish_marks():
+        info["protocol_ms"] = {b[0]: round((b[1] - a[1]) * 1e3, 3) for a, b in zip(marks, marks[1:])}
+
     if rank != 0:
         comm.send_piece(0, piece, (nbits + 7) // 8)
+        mark("send_piece")
+        finish_marks()
         return None, info
     stream = backend.new_stream(nbytes)
     header = bytes([0x42, 0x5A, 0x68, 0x30 + level])
@@ -270,7 +307,11 @@ def compress_sharded(backend, comm, region, shard_len, level, stream_ends_in_reg
     trailer = (0x177245385090 << 32) | comb
     backend.place(stream, offs[-1], trailer.to_bytes(10, "big"), 80)
     info["combined_crc"] = comb
-    return (backend.to_host(stream, nbytes) if return_host else stream), info
+    mark("assemble")
+    out = backend.to_host(stream, nbytes) if return_host else stream
+    mark("to_host")
+    finish_marks()
+    return out, info
 
 
 class TorchComm:

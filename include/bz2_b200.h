@@ -99,12 +99,15 @@ int  bz2b200_stream_feed(bz2b200_engine* e, const void* src, size_t n, int end_m
  *   scan_create   chunk structure of d_src[0,n).  prev_byte / prev_run: the byte before d_src[0]
  *                 and the length of the run it ends (256 / 0 at the start of the stream);
  *                 input_ends: the stream ends at n.
+ *   scan_rescan   the same for a new region of at most the size the scan was created for, reusing
+ *                 its buffers (a step loop pays no allocation).
  *   scan_boundary first block boundary >= limit when blocks are laid from the boundary `start`;
  *                 also the number of blocks in [start, boundary).
  *   concat_bits   S5: OR `nbits` bits of d_src (from bit 0) into d_dst at bit offset dst_bit.     */
 typedef struct bz2b200_scan bz2b200_scan;
 int  bz2b200_scan_create(bz2b200_scan** out, int device, int block_size_100k, const void* d_src, size_t n,
                          int prev_byte, uint64_t prev_run, int input_ends);
+int  bz2b200_scan_rescan(bz2b200_scan* s, const void* d_src, size_t n, int prev_byte, uint64_t prev_run, int input_ends);
 int  bz2b200_scan_boundary(bz2b200_scan* s, size_t start, size_t limit, unsigned flags,
                            size_t* boundary, uint32_t* n_blocks);
 void bz2b200_scan_destroy(bz2b200_scan* s);
