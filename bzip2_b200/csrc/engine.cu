@@ -114,6 +114,10 @@ static int engine_new(EngineFull** out, int device, int level, size_t window_byt
       e->s2_group = g ? (u32)atoi(g) : 0;
       const char* tf = getenv("BZ2_B200_TEXT_FIRST");
       e->text_first = tf ? (u32)atoi(tf) : 1;
+      const char* r8 = getenv("BZ2_B200_RADIX_C8K");
+      e->radix_c8k = r8 ? (u32)atoi(r8) : 1;
+      const char* rx = getenv("BZ2_B200_RADIX_MIN");
+      e->radix_min = rx ? (u32)atoi(rx) : 128;
       const char* kg = getenv("BZ2_B200_KG_MODE");
       e->kg_mode = kg ? (u32)atoi(kg) : 1;
       const char* ss = getenv("BZ2_B200_S2_STREAMS");
@@ -141,6 +145,7 @@ static int engine_new(EngineFull** out, int device, int level, size_t window_byt
          if (c0 == cudaSuccess) c0 = cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming);
          if (c0 != cudaSuccess) { rc = engine_fail(e, c0, __FILE__, __LINE__); goto fail; }
       }
+      if (stage2_init() != 0) { rc = engine_fail(e, cudaGetLastError(), __FILE__, __LINE__); goto fail; }
       c0 = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
       if (c0 != cudaSuccess) { rc = engine_fail(e, c0, __FILE__, __LINE__); goto fail; }
       ALLOC(e->enc, E + 64); ALLOC(e->cend, E + 64);
@@ -171,7 +176,7 @@ static int engine_new(EngineFull** out, int device, int level, size_t window_byt
       ALLOC(e->bt.bits, B); ALLOC(e->bt.bitoff, B + 2);
       static const u32 minlen[N_SMALL_CLASSES] = {2, 3, 5, 9, 17};
       for (int c = 0; c < N_SMALL_CLASSES; c++) e->lists.small_cap[c] = (u32)(E / minlen[c] + 1024);
-      static const u32 bigmin[N_BIG_CLASSES] = {33, 257, 513, 1025, 2049, 4097};
+      static const u32 bigmin[N_BIG_CLASSES] = {33, 257, 513, 1025, 2049, 4097, 8193};
       for (int c = 0; c < N_BIG_CLASSES; c++) e->lists.big_cap[c] = (u32)(E / bigmin[c] + 1024);
       for (int w = 0; w < 2; w++) {
          for (int c = 0; c < N_SMALL_CLASSES; c++) ALLOC(e->lists.small_items[w][c], e->lists.small_cap[c]);

@@ -18,15 +18,16 @@
 namespace bz {
 
 constexpr int N_SMALL_CLASSES = 5;          // segment lengths 2, 3-4, 5-8, 9-16, 17-32
-constexpr int N_BIG_CLASSES = 6;            // u64 worklists
+constexpr int N_BIG_CLASSES = 7;            // u64 worklists
 constexpr int CLS_W256 = 5;                 // 33..256    one warp, registers + shuffles
 constexpr int CLS_C512 = 6;                 // 257..512   CTA of 64
 constexpr int CLS_C1K = 7;                  // 513..1024  CTA of 128
 constexpr int CLS_C2K = 8;                  // 1025..2048 CTA of 256
 constexpr int CLS_C4K = 9;                  // 2049..4096 CTA of 512
-constexpr int CLS_LARGE = 10;               // > 4096     CTA of 1024, radix passes in HBM
-constexpr int N_CLASSES = 11;
-constexpr u32 MED_MAX = 4096;
+constexpr int CLS_C8K = 10;                 // 4097..8192 CTA of 1024
+constexpr int CLS_LARGE = 11;               // > 8192     CTA of 1024, radix passes in HBM
+constexpr int N_CLASSES = 12;
+constexpr u32 MED_MAX = 8192;
 constexpr u32 MAX_BLOCKS = 4096;            // block id must fit 12 bits in a segment entry
 constexpr u32 MAX_ENC = 1u << 27;           // flat position must fit 27 bits in a small entry
 
@@ -76,6 +77,7 @@ int scan_boundary(ScanState* s, u32 start, u32 limit, u32 tail_merge, u32* bound
 
 // ---- stage launchers (each returns 0 or a negative error; all work on e->stream) ----
 int stage1_run(Engine* e, const u8* d_in, u32 W, bool is_final, bool tail_merge, u32* nb_out, u32* consumed_out, u32* enc_total_out);
+int stage2_init();
 int stage2_run(Engine* e, u32 nb, u32 E);
 int stage3_run(Engine* e, u32 nb, u32 E);
 int stage4_run(Engine* e, u32 nb, u32 E, u8* d_out, u64 origin_bit, u64 start_bit, u64* end_bit_out);
@@ -110,6 +112,8 @@ struct Engine {
    u32 *kk, *nbins, *hh, *kbits, *ksym;   // [blk_cap]
    u64 *K, *kscrA, *kscrB; // [E] packed text keys; 64-bit key scratch of the large path
    u32 text_first;         // first refinement round sorts by text keys (default on)
+   u32 radix_c8k;          // 4097..8192: 1 = shared-memory radix CTA of 1024, 0 = the HBM radix path of the large class
+   u32 radix_min;          // CTA sort classes with at least this many threads use radix passes (1024 = none)
    u32 kg_mode;            // k-gram bucket sort: 0 = count / rank / atomic scatter, 1 = count with arrival index / place
    u32 s2_streams;         // run the size classes of a refinement round on side streams (default on)
    cudaStream_t aux[3];    // side streams of the BWT rounds

@@ -68,7 +68,7 @@ __device__ __forceinline__ int seg_class(u32 len)
    if (len <= 32) return 31 - __clz(len - 1);
    if (len <= 256) return CLS_W256;
    if (len > MED_MAX) return CLS_LARGE;
-   return CLS_C512 + (23 - __clz(len - 1));     // 257..512 -> +0, ..1024 -> +1, ..2048 -> +2, ..4096 -> +3
+   return CLS_C512 + (23 - __clz(len - 1));     // 257..512 -> +0, ..1024 -> +1, ..2048 -> +2, ..4096 -> +3, ..8192 -> +4
 }
 
 // Rank words carry two generations so that a refinement round can update ranks in place while
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(256) k_codemap(S2Params p)
       p.nbins[b] = bins;
       u32 bits = 1;
       while ((1u << bits) < tot) bits++;
-      u32 m = 52u / bits;
+      u32 m = 51u / bits;                       // 51 key bits + 13 local-index bits fill a packed 64-bit sort word
       if (m > 48u) m = 48u;
       p.hh[b] = k + m;
       p.kbits[b] = m * bits;
@@ -507,6 +507,174 @@ k_refine_medium(S2Params p, ListsDev Lout, const u64* items, u32 count, u32 roun
    }
 }
 
+// ---- 2b'. CTA-resident LSD radix sort of the same packed words ---------------------------------
+// For segments of 513..4096 elements the bitonic network costs ~1000 instructions per element;
+// eight-bit radix passes over a shared-memory copy cost ~30 per element and pass, and digits on
+// which every key of the segment agrees are skipped (the rule on periodic data).  A pass ranks each
+// element inside its warp with match_any (stable), the per-warp digit counts are scanned over
+// warps and bins, and the elements -- held in registers meanwhile -- are written back in place.
+template <int THREADS, bool TEXT>
+__global__ void __launch_bounds__(THREADS) k_refine_radix(S2Params p, ListsDev Lout, const u64* items, u32 count, u32 round)
+{
+   constexpr int CAP = THREADS * MS_ITEMS;
+   constexpr int LBITS = (CAP > 4096) ? 13 : 12;     // local index bits under the key
+   typedef typename KeyOf<(TEXT || CAP > 4096)>::type VT;   // packed word: key << LBITS | local
+   constexpr int WARPS = THREADS / 32;
+   constexpr int BPT = (256 + THREADS - 1) / THREADS;   // bins per thread in the scan step
+   extern __shared__ __align__(16) unsigned char dyn_smem[];
+   VT* const buf = reinterpret_cast<VT*>(dyn_smem);   // [CAP]
+   __shared__ u16 whist[WARPS][256];            // counts and prefixes stay below CAP <= 4096
+   __shared__ u32 binbase[256];
+   __shared__ u32 ssm[34];
+   __shared__ VT s_red[2][WARPS];
+   const u32 t = threadIdx.x, w = t >> 5, l = lane_id();
+   const u64 entry = items[blockIdx.x];
+   const u32 pos = (u32)(entry >> 32);
+   const u32 b = (u32)(entry >> 20) & 0xfffu;
+   const u32 len = (u32)entry & 0xfffffu;
+   const u32 xb = p.X[b], n = p.X[b + 1] - xb;
+   u32 depth;
+   const u32 shift = round_shift(p, b, round, &depth);
+
+   // striped load: warp w owns positions w*256 .. w*256+255, lane l takes every 32nd of them
+   VT v[MS_ITEMS];
+   VT vand = ~(VT)0, vor = 0;
+#pragma unroll
+   for (int k = 0; k < MS_ITEMS; k++) {
+      const u32 i = w * (32 * MS_ITEMS) + (u32)k * 32 + l;
+      VT word = ~(VT)0;
+      if (i < len) {
+         const u32 idx = p.sa[pos + i];
+         word = ((VT)load_key<TEXT>(p, xb, n, idx, shift, round + 1) << LBITS) | (VT)i;
+         vand &= word; vor |= word;
+      }
+      v[k] = word;
+      buf[i] = word;
+   }
+   // digits on which all keys agree need no pass
+#pragma unroll
+   for (int d = 16; d > 0; d >>= 1) {
+      vand &= __shfl_xor_sync(FULL, vand, d);
+      vor |= __shfl_xor_sync(FULL, vor, d);
+   }
+   if (l == 0) { s_red[0][w] = vand; s_red[1][w] = vor; }
+   __syncthreads();
+   {
+      VT a = ~(VT)0, o = 0;
+#pragma unroll
+      for (int k = 0; k < WARPS; k++) { a &= s_red[0][k]; o |= s_red[1][k]; }
+      vand = a; vor = o;
+   }
+   const VT diff = (vand ^ vor) >> LBITS;         // key bits that vary inside the segment
+   const int npass = TEXT ? (int)((p.kbits[b] + 7) >> 3) : 3;
+
+   for (int pass = 0; pass < npass; pass++) {
+      const int sh = LBITS + 8 * pass;
+      if (((diff >> (8 * pass)) & 255) == 0) continue;
+#pragma unroll
+      for (int k = 0; k < 8; k++) whist[w][l * 8 + k] = 0;
+      __syncwarp();
+      u32 rk[MS_ITEMS];
+#pragma unroll
+      for (int k = 0; k < MS_ITEMS; k++) {
+         const u32 d = (u32)(v[k] >> sh) & 255;
+         const u32 m = __match_any_sync(FULL, d);
+         const u32 old = whist[w][d];
+         __syncwarp();
+         if (l == (u32)(__ffs(m) - 1)) whist[w][d] = (u16)(old + __popc(m));
+         __syncwarp();
+         rk[k] = old + __popc(m & lanemask_lt());
+      }
+      __syncthreads();
+      // per bin: exclusive prefix over the warps, bin total
+      u32 tot[BPT];
+#pragma unroll
+      for (int q = 0; q < BPT; q++) {
+         const u32 bin = t + (u32)q * THREADS;
+         u32 run = 0;
+         if (bin < 256) {
+#pragma unroll
+            for (int ww = 0; ww < WARPS; ww++) { const u32 c = whist[ww][bin]; whist[ww][bin] = (u16)run; run += c; }
+         }
+         tot[q] = run;
+      }
+      // exclusive scan of the 256 bin totals (bins are laid out bin = t + q*THREADS)
+      if (THREADS >= 256) {
+         u32 dummy;
+         const u32 ex = block_excl_sum<THREADS>(t < 256 ? tot[0] : 0u, ssm, &dummy);
+         if (t < 256) binbase[t] = ex;
+      } else {
+         // THREADS = 128 or 64: scan the q-slices one after the other
+         u32 carry = 0;
+#pragma unroll
+         for (int q = 0; q < BPT; q++) {
+            u32 total;
+            const u32 ex = block_excl_sum<THREADS>(tot[q], ssm, &total);
+            binbase[t + (u32)q * THREADS] = carry + ex;
+            carry += total;
+            __syncthreads();
+         }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < MS_ITEMS; k++) {
+         const u32 d = (u32)(v[k] >> sh) & 255;
+         buf[binbase[d] + whist[w][d] + rk[k]] = v[k];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < MS_ITEMS; k++) v[k] = buf[w * (32 * MS_ITEMS) + (u32)k * 32 + l];
+   }
+   __syncthreads();
+
+   // blocked view of the sorted sequence: thread t owns positions t*8 .. t*8+7
+   const u32 base = t * MS_ITEMS;
+#pragma unroll
+   for (int r = 0; r < MS_ITEMS; r++) v[r] = buf[base + r];
+   const VT prevlast = buf[base ? base - 1 : 0];
+   const VT nextfirst = buf[(base + MS_ITEMS < (u32)CAP) ? base + MS_ITEMS : (u32)CAP - 1];
+   u32 last = 0, gs[MS_ITEMS];
+#pragma unroll
+   for (int r = 0; r < MS_ITEMS; r++) {
+      const u32 e = base + r;
+      if (e < len) {
+         const VT pv = (r == 0) ? prevlast : v[r - 1];
+         if (e == 0 || (pv >> LBITS) != (v[r] >> LBITS)) last = e + 1;
+      }
+      gs[r] = last;
+   }
+   const u32 incl = block_incl_max<THREADS>(last, ssm);
+   u32 prev = __shfl_up_sync(FULL, incl, 1);
+   if (l == 0) prev = ssm[w];
+   u32 idxs[MS_ITEMS];
+#pragma unroll
+   for (int r = 0; r < MS_ITEMS; r++) {
+      const u32 e = base + r;
+      const u32 local = (u32)v[r] & ((1u << LBITS) - 1u);
+      idxs[r] = (e < len) ? p.sa[pos + local] : 0;
+   }
+   __syncthreads();
+   const bool deep = (depth >= n);
+#pragma unroll
+   for (int r = 0; r < MS_ITEMS; r++) {
+      const u32 e = base + r;
+      const bool in = e < len;
+      u32 g = gs[r] ? gs[r] : prev;
+      g = g ? g - 1 : 0;
+      bool is_end = false;
+      if (in) {
+         p.sa[pos + e] = idxs[r];
+         p.rank[xb + idxs[r]] = rk_pack(round + 1, pos - xb, (pos - xb) + g);
+         const VT nx = (r == MS_ITEMS - 1) ? nextfirst : v[r + 1];
+         is_end = (e == len - 1) || ((nx >> LBITS) != (v[r] >> LBITS));
+      }
+      const u32 size = e - g + 1;
+      const bool multi = in && is_end && size >= 2;
+      if (multi && deep) atomicMax(&p.power_q[b], size);
+      push_seg(Lout, multi && !deep, pos + g, b, size);
+   }
+}
+
 // ---- 2c. large segments: one CTA, stable LSD radix passes ----------------------------
 constexpr int LG_THREADS = 1024;
 constexpr int LG_ITEMS = 4;
@@ -737,6 +905,23 @@ static void launch_medium(Engine* e, cudaStream_t st, const S2Params& p, const L
    char nm[64]; snprintf(nm, sizeof nm, "k_refine_medium<%d,%d> count=%u round=%u", THREADS, (int)text, count, round); dbg_sync(e, nm);
 }
 
+template <int THREADS>
+static void launch_radix(Engine* e, cudaStream_t st, const S2Params& p, const ListsDev& Lout, const u64* items, u32 count, u32 round, bool text)
+{
+   constexpr size_t CAP = (size_t)THREADS * MS_ITEMS;
+   if (text) k_refine_radix<THREADS, true><<<count, THREADS, CAP * sizeof(u64), st>>>(p, Lout, items, count, round);
+   else      k_refine_radix<THREADS, false><<<count, THREADS, CAP * (CAP > 4096 ? sizeof(u64) : sizeof(u32)), st>>>(p, Lout, items, count, round);
+   char nm[64]; snprintf(nm, sizeof nm, "k_refine_radix<%d,%d> count=%u round=%u", THREADS, (int)text, count, round); dbg_sync(e, nm);
+}
+
+// the 8192-element radix sort keeps 64 KiB of sort words in dynamic shared memory
+int stage2_init()
+{
+   cudaError_t c = cudaFuncSetAttribute(k_refine_radix<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * (int)sizeof(u64));
+   if (c == cudaSuccess) c = cudaFuncSetAttribute(k_refine_radix<1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * (int)sizeof(u64));
+   return c == cudaSuccess ? 0 : -1;
+}
+
 int stage2_run(Engine* e, u32 nb, u32 E)
 {
    cudaStream_t st = e->stream;
@@ -829,14 +1014,20 @@ int stage2_run(Engine* e, u32 nb, u32 E)
             for (int a = 0; a < 3; a++) BZ_CUDA(e, cudaStreamWaitEvent(e->aux[a], e->ev_fork, 0));
          }
          if (cnt[CLS_LARGE]) {
-            if (text) k_refine_large<true><<<cnt[CLS_LARGE], LG_THREADS, 0, sL>>>(p, Lout, bi[5], round);
-            else      k_refine_large<false><<<cnt[CLS_LARGE], LG_THREADS, 0, sL>>>(p, Lout, bi[5], round);
+            if (text) k_refine_large<true><<<cnt[CLS_LARGE], LG_THREADS, 0, sL>>>(p, Lout, bi[6], round);
+            else      k_refine_large<false><<<cnt[CLS_LARGE], LG_THREADS, 0, sL>>>(p, Lout, bi[6], round);
             dbg_sync(e, "k_refine_large");
          }
-         if (cnt[CLS_C4K])   launch_medium<512>(e, sM, p, Lout, bi[4], cnt[CLS_C4K], round, text);
-         if (cnt[CLS_C2K])   launch_medium<256>(e, sM, p, Lout, bi[3], cnt[CLS_C2K], round, text);
-         if (cnt[CLS_C1K])   launch_medium<128>(e, sW, p, Lout, bi[2], cnt[CLS_C1K], round, text);
-         if (cnt[CLS_C512])  launch_medium<64>(e, sW, p, Lout, bi[1], cnt[CLS_C512], round, text);
+         if (cnt[CLS_C8K]) {
+            if (e->radix_c8k) launch_radix<1024>(e, sL, p, Lout, bi[5], cnt[CLS_C8K], round, text);
+            else if (text) k_refine_large<true><<<cnt[CLS_C8K], LG_THREADS, 0, sL>>>(p, Lout, bi[5], round);
+            else           k_refine_large<false><<<cnt[CLS_C8K], LG_THREADS, 0, sL>>>(p, Lout, bi[5], round);
+         }
+         const u32 rx = e->radix_min;            // smallest CTA class sorted by radix passes instead of the bitonic network
+         if (cnt[CLS_C4K])   { if (rx <= 512) launch_radix<512>(e, sM, p, Lout, bi[4], cnt[CLS_C4K], round, text); else launch_medium<512>(e, sM, p, Lout, bi[4], cnt[CLS_C4K], round, text); }
+         if (cnt[CLS_C2K])   { if (rx <= 256) launch_radix<256>(e, sM, p, Lout, bi[3], cnt[CLS_C2K], round, text); else launch_medium<256>(e, sM, p, Lout, bi[3], cnt[CLS_C2K], round, text); }
+         if (cnt[CLS_C1K])   { if (rx <= 128) launch_radix<128>(e, sW, p, Lout, bi[2], cnt[CLS_C1K], round, text); else launch_medium<128>(e, sW, p, Lout, bi[2], cnt[CLS_C1K], round, text); }
+         if (cnt[CLS_C512])  { if (rx <= 64)  launch_radix<64>(e, sW, p, Lout, bi[1], cnt[CLS_C512], round, text);  else launch_medium<64>(e, sW, p, Lout, bi[1], cnt[CLS_C512], round, text); }
          if (cnt[CLS_W256])  launch_medium<32>(e, sW, p, Lout, bi[0], cnt[CLS_W256], round, text);
          if (cnt[4]) launch_small<32>(e, st, p, Lout, si[4], cnt[4], round, text);
          if (cnt[3]) launch_small<16>(e, st, p, Lout, si[3], cnt[3], round, text);

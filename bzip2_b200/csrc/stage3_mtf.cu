@@ -170,7 +170,9 @@ __global__ void __launch_bounds__(MTF_CTA) k_mtf_encode(S3Params p)
    const u32* in32 = reinterpret_cast<const u32*>(p.bwt + (start - a));
    u32* out32 = reinterpret_cast<u32*>(p.z + (start - a));
    u8* my = lst + tid;
-   u32 front = my[0];
+   // the first four list entries live in registers (on BWT output most symbols hit one of them);
+   // shared-memory rows 4..255 hold the rest of the list, rows 0..3 are dead after this load
+   u32 l0 = my[0], l1 = my[MTF_CTA], l2 = my[2 * MTF_CTA], l3 = my[3 * MTF_CTA];
    u32 lead = 0, run = 0, inner = 0;
    bool seen_nz = false;
    const u32 nwords = (size + a + 3) >> 2;
@@ -182,10 +184,12 @@ __global__ void __launch_bounds__(MTF_CTA) k_mtf_encode(S3Params p)
          const i32 i = (i32)(w * 4 + k) - (i32)a;
          if (i < 0 || i >= (i32)size) continue;
          const u32 c = (word >> (8 * k)) & 0xff;
-         u32 pos = 0;
-         if (c != front) {
-            u32 prev = front;
-            u32 j = 1;
+         const bool e0 = (c == l0), e1 = (c == l1), e2 = (c == l2), e3 = (c == l3);
+         u32 pos = e0 ? 0u : e1 ? 1u : e2 ? 2u : 3u;
+         if (!(e0 | e1 | e2 | e3)) {
+            // deeper than the register window: shift rows 4..j-1 down by one while searching
+            u32 prev = l3;
+            u32 j = 4;
             for (;;) {
                const u32 cur = my[j * MTF_CTA];
                my[j * MTF_CTA] = (u8)prev;
@@ -193,10 +197,13 @@ __global__ void __launch_bounds__(MTF_CTA) k_mtf_encode(S3Params p)
                prev = cur;
                j++;
             }
-            my[0] = (u8)c;
-            front = c;
             pos = j;
          }
+         // move-to-front inside the register window (a miss shifts the whole window, like a hit at 3)
+         l3 = (e0 | e1 | e2) ? l3 : l2;
+         l2 = (e0 | e1) ? l2 : l1;
+         l1 = e0 ? l1 : l0;
+         l0 = c;
          zword |= pos << (8 * k);
          if (pos == 0) run++;
          else {
