@@ -233,7 +233,7 @@ def sharded_bench(args, torch, dist, B, rank, world, local_rank, dev, data, n, m
     value = world * n / (ms_per_step * 1e-3) / 1e6
     e2e = None
     if not args.no_e2e:
-        for _ in range(max(1, min(args.warmup, 2))):
+        for _ in range(max(1, args.warmup)):
             host_out, info = one(False)
         e_dev_s, e_wall_s, (host_out, info) = timed(False, args.steps)
         e_proto = [None] * world
@@ -386,7 +386,7 @@ def main():
         lib = B.load()
         # BZ2_bzBuffToBuffCompress takes 32-bit lengths; the engine pool keeps the HBM allocation between calls
         dlen = C.c_uint(min(cap, 0xFFFFFFFF))
-        for _ in range(max(1, min(args.warmup, 2))):
+        for _ in range(max(1, args.warmup)):
             dlen = C.c_uint(min(cap, 0xFFFFFFFF))
             rc = lib.BZ2_bzBuffToBuffCompress(h_out.data_ptr(), C.byref(dlen), h_in.data_ptr(), n, args.level, 0, 0)
             assert rc == 0, rc
@@ -434,9 +434,9 @@ def main():
     except Exception:  # noqa: BLE001
         pass
     roof = {"bound": "hbm",
-            "kernel": "S2 BWT kernel family (k_kgram*, k_refine_*, k_bwt_out; ~65 launches per 100 MB window), timed live by CUDA events "
-                      "around the stage on the launching stream; top single kernel k_refine_large<true> = 12% of the step "
-                      "(profiles/r01_final_launch_summary_text100MB.md)",
+            "kernel": "S2 BWT kernel family (k_kgram*, k_refine_*, k_bwt_out; ~70 launches per 100 MB window), timed live by CUDA events "
+                      "around the stage on the launching stream; top single kernel k_refine_large<true> = 10% of the step "
+                      "(profiles/r01_v3_launch_summary_text100MB.md)",
             "algorithmic_bytes": int(s2_bytes), "algorithmic_rule": "2*rho bytes per input byte: read the block once, write the last column once (SURVEY 8d)",
             "achieved": round(s2_bytes / (stage_ms[2] * 1e-3) / 1e9, 3), "peak": peak, "unit": "GB/s",
             "frac": round(s2_bytes / (stage_ms[2] * 1e-3) / 1e9 / peak, 6), "traffic": traffic, "peak_source": peak_src,
