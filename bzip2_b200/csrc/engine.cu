@@ -9,6 +9,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <new>
+#include <pthread.h>
 
 namespace bz {
 
@@ -41,8 +42,25 @@ struct StreamState {
    bz2b200_stats st;
 };
 
+// Streaming feed (bz2b200_stream_feed): the caller's thread only copies input into a pinned ring; a worker
+// thread owned by the engine cuts windows out of it and runs them, so feeding (fread / memcpy in the client)
+// overlaps the GPU work (the reference's BZ2_bzWrite trickle, bzlib.c:1049-1066).
+struct AsyncFeed {
+   pthread_t th;
+   pthread_mutex_t mu;
+   pthread_cond_t cv_work, cv_space, cv_done;
+   bool inited, th_started;
+   size_t cap;                 // ring capacity in bytes (the ring is h_in)
+   u64 head, tail;             // absolute byte counters: the ring holds stream bytes [head, tail)
+   int pending_end;            // closing request posted by the feeding thread: 1 = flush, 2 = finish
+   bool closing_done, busy, quit, hook_advanced;
+   int err;
+   u8* outq; size_t out_len, out_cap;   // compressed bytes produced by the worker, drained by the feeding thread
+};
+
 struct EngineFull : Engine {
    StreamState ss;
+   AsyncFeed af;
    bool debug_keep;
    u32 last_nb, last_E;
    cudaEvent_t ev[6];
@@ -62,9 +80,12 @@ static cudaError_t dalloc(T** p, size_t count)
 
 #define ALLOC(ptr, count) do { cudaError_t c_ = dalloc(&(ptr), (size_t)(count)); if (c_ != cudaSuccess) { rc = engine_fail(e, c_, __FILE__, __LINE__); goto fail; } } while (0)
 
+static void feed_shutdown(EngineFull* e);
+
 static void engine_free(EngineFull* e)
 {
    if (!e) return;
+   feed_shutdown(e);
    cudaSetDevice(e->device);
    void* dev[] = { e->enc, e->cend, e->sa, e->rank, e->keyA, e->keyB, e->idxB, e->bwt, e->z, e->mtfv, e->hist,
                    e->blockmap, e->code, e->kk, e->nbins, e->hh, e->kbits, e->ksym, e->K, e->kscrA, e->kscrB, e->tile_len, e->tile_ext, e->tile_carry, e->tile_size, e->tile_base, e->s1_scalars,
@@ -211,7 +232,11 @@ static int ensure_staging(EngineFull* e, bool need_hin)
       if (c != cudaSuccess) return engine_fail(e, c, __FILE__, __LINE__);
       for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&e->ev_h2d[i], cudaEventDisableTiming);
    }
-   if (need_hin && !e->h_in) { cudaError_t c = cudaMallocHost(reinterpret_cast<void**>(&e->h_in), (size_t)e->win_cap); if (c != cudaSuccess) return engine_fail(e, c, __FILE__, __LINE__); }
+   if (need_hin && !e->h_in) {
+      e->af.cap = (size_t)e->win_cap + (size_t)e->win_cap / 2;
+      cudaError_t c = cudaMallocHost(reinterpret_cast<void**>(&e->h_in), e->af.cap);
+      if (c != cudaSuccess) return engine_fail(e, c, __FILE__, __LINE__);
+   }
    return 0;
 }
 
@@ -361,6 +386,155 @@ static int begin_stream(EngineFull* e, Sink& sk)
    if (ss.header_done) return 0;
    ss.header_done = true;
    return host_put_bits(e, sk, 0x425A6830u + (u32)e->level, 32);            // compress.c:841-845  "BZh" '0'+level
+}
+
+// ---- asynchronous streaming feed -----------------------------------------------------------------
+static int feed_queue_sink(void* user, const void* bytes, size_t n)
+{
+   EngineFull* e = static_cast<EngineFull*>(user);
+   AsyncFeed& a = e->af;
+   pthread_mutex_lock(&a.mu);
+   if (a.out_len + n > a.out_cap) {
+      size_t nc = a.out_cap ? a.out_cap : ((size_t)1 << 20);
+      while (nc < a.out_len + n) nc *= 2;
+      u8* nb = static_cast<u8*>(realloc(a.outq, nc));
+      if (!nb) { pthread_mutex_unlock(&a.mu); return BZ2B200_ENOMEM; }
+      a.outq = nb; a.out_cap = nc;
+   }
+   memcpy(a.outq + a.out_len, bytes, n);
+   a.out_len += n;
+   pthread_mutex_unlock(&a.mu);
+   return 0;
+}
+
+// stage 1 has fixed how much of the window this pass consumes and the H2D copy is complete: release the ring space
+static void feed_after_s1(EngineFull* e, u32 consumed, void*)
+{
+   AsyncFeed& a = e->af;
+   pthread_mutex_lock(&a.mu);
+   a.head += consumed;
+   a.hook_advanced = true;
+   pthread_cond_broadcast(&a.cv_space);
+   pthread_mutex_unlock(&a.mu);
+}
+
+static int feed_run_window(EngineFull* e, u64 head, u32 W, bool closing, int end_mode, bool tail_running, u32* cons)
+{
+   AsyncFeed& a = e->af;
+   Sink sk; sk.fn = feed_queue_sink; sk.user = e; sk.dst = nullptr; sk.cap = 0; sk.len = 0;
+   int rc = begin_stream(e, sk);
+   if (rc) return rc;
+   if (W) {
+      const size_t pos = (size_t)(head % a.cap);
+      const size_t first = (W < a.cap - pos) ? W : a.cap - pos;
+      BZ_CUDA(e, cudaMemcpyAsync(e->d_in, e->h_in + pos, first, cudaMemcpyHostToDevice, e->stream));
+      if (W > first) BZ_CUDA(e, cudaMemcpyAsync(e->d_in + first, e->h_in, W - first, cudaMemcpyHostToDevice, e->stream));
+      e->after_s1 = feed_after_s1;
+      e->after_s1_ctx = nullptr;
+      rc = window_to_sink(e, e->d_in, W, closing, closing && !tail_running, sk, cons);
+      e->after_s1 = nullptr;
+      if (rc) return rc;
+      if (*cons == 0 && !closing) return set_err(BZ2B200_EINTERNAL, "window made no progress");
+   }
+   if (closing && end_mode == 2) rc = finish_stream(e, sk);
+   return rc;
+}
+
+static void* feed_worker(void* arg)
+{
+   EngineFull* e = static_cast<EngineFull*>(arg);
+   AsyncFeed& a = e->af;
+   cudaSetDevice(e->device);
+   pthread_mutex_lock(&a.mu);
+   for (;;) {
+      while (!a.quit && (a.err || !((a.tail - a.head >= e->win_cap) || (a.pending_end && !a.closing_done))))
+         pthread_cond_wait(&a.cv_work, &a.mu);
+      if (a.quit) break;
+      const u64 avail = a.tail - a.head;
+      const int end_mode = a.pending_end;
+      const bool closing = end_mode != 0 && avail <= e->win_cap;
+      const u32 W = (u32)(avail < e->win_cap ? avail : e->win_cap);
+      const u64 head = a.head;
+      const bool tail_running = e->ss.tail_running;
+      a.busy = true;
+      a.hook_advanced = false;
+      pthread_mutex_unlock(&a.mu);
+      u32 cons = 0;
+      const int rc = feed_run_window(e, head, W, closing, end_mode, tail_running, &cons);
+      pthread_mutex_lock(&a.mu);
+      if (!a.hook_advanced) a.head += cons;
+      a.busy = false;
+      if (rc) a.err = rc;
+      if (closing || rc) a.closing_done = true;
+      pthread_cond_broadcast(&a.cv_space);
+      pthread_cond_broadcast(&a.cv_done);
+   }
+   pthread_mutex_unlock(&a.mu);
+   return nullptr;
+}
+
+static int feed_start(EngineFull* e)
+{
+   AsyncFeed& a = e->af;
+   if (!a.inited) {
+      pthread_mutex_init(&a.mu, nullptr);
+      pthread_cond_init(&a.cv_work, nullptr);
+      pthread_cond_init(&a.cv_space, nullptr);
+      pthread_cond_init(&a.cv_done, nullptr);
+      a.inited = true;
+   }
+   if (!a.th_started) {
+      a.quit = false;
+      if (pthread_create(&a.th, nullptr, feed_worker, e) != 0) return set_err(BZ2B200_ENOMEM, "cannot start the feed thread");
+      a.th_started = true;
+   }
+   return 0;
+}
+
+static void feed_shutdown(EngineFull* e)
+{
+   AsyncFeed& a = e->af;
+   if (a.th_started) {
+      pthread_mutex_lock(&a.mu);
+      a.quit = true;
+      pthread_cond_broadcast(&a.cv_work);
+      pthread_mutex_unlock(&a.mu);
+      pthread_join(a.th, nullptr);
+      a.th_started = false;
+   }
+   if (a.inited) {
+      pthread_mutex_destroy(&a.mu);
+      pthread_cond_destroy(&a.cv_work); pthread_cond_destroy(&a.cv_space); pthread_cond_destroy(&a.cv_done);
+      a.inited = false;
+   }
+   free(a.outq);
+   a.outq = nullptr; a.out_len = a.out_cap = 0;
+}
+
+// a new stream starts: wait for a window the previous (abandoned) stream may still have in flight, then forget it
+static void feed_reset(EngineFull* e)
+{
+   AsyncFeed& a = e->af;
+   if (!a.inited) return;
+   pthread_mutex_lock(&a.mu);
+   while (a.busy) pthread_cond_wait(&a.cv_done, &a.mu);
+   a.head = a.tail = 0;
+   a.pending_end = 0; a.closing_done = false; a.err = 0; a.out_len = 0;
+   pthread_mutex_unlock(&a.mu);
+}
+
+// hand the compressed bytes the worker has produced so far to the caller's sink (on the caller's thread)
+static int feed_drain(EngineFull* e, bz2b200_sink sink, void* user)
+{
+   AsyncFeed& a = e->af;
+   pthread_mutex_lock(&a.mu);
+   u8* buf = a.outq; const size_t n = a.out_len;
+   if (n == 0) { pthread_mutex_unlock(&a.mu); return 0; }
+   a.outq = nullptr; a.out_len = a.out_cap = 0;          // the worker starts a fresh queue
+   pthread_mutex_unlock(&a.mu);
+   const int rc = sink(user, buf, n);
+   free(buf);
+   return rc;
 }
 
 // Makes the engine's device current for the duration of a C-ABI call and restores the caller's.
@@ -522,6 +696,7 @@ int bz2b200_stream_begin(bz2b200_engine* h)
    DeviceGuard guard(e->device);
    int rc = ensure_staging(e, true);
    if (rc) return rc;
+   feed_reset(e);
    stream_reset(e);
    return 0;
 }
@@ -531,38 +706,45 @@ int bz2b200_stream_feed(bz2b200_engine* h, const void* src, size_t n, int end_mo
    EngineFull* e = reinterpret_cast<EngineFull*>(h);
    if (!e || !sink || (!src && n) || end_mode < 0 || end_mode > 2) return set_err(BZ2B200_EPARAM, "bad argument");
    if (!e->h_in) return set_err(BZ2B200_EPARAM, "bz2b200_stream_begin was not called");
-   DeviceGuard guard(e->device);
-   e->after_s1 = nullptr;
-   StreamState& ss = e->ss;
-   Sink sk; sk.fn = sink; sk.user = user; sk.dst = nullptr; sk.cap = 0; sk.len = 0;
-   int rc;
-   if ((rc = begin_stream(e, sk))) return rc;
+   int rc = feed_start(e);
+   if (rc) return rc;
+   AsyncFeed& a = e->af;
+   if ((rc = feed_drain(e, sink, user))) return rc;
    const u8* in = static_cast<const u8*>(src);
-   if (n) ss.tail_running = (end_mode == 0);
-   ss.st.in_bytes += n;
    size_t off = 0;
-   for (;;) {
-      const size_t room = (size_t)e->win_cap - ss.h_fill;
-      const size_t take = (n - off < room) ? (n - off) : room;
-      if (take) { memcpy(e->h_in + ss.h_fill, in + off, take); ss.h_fill += take; off += take; }
-      const bool all_in = (off == n);
-      const bool closing = (end_mode != 0) && all_in;
-      if (ss.h_fill < e->win_cap && !closing) break;          // wait for more input
-      if (ss.h_fill == 0) break;
-      BZ_CUDA(e, cudaMemcpyAsync(e->d_in, e->h_in, ss.h_fill, cudaMemcpyHostToDevice, e->stream));
-      u32 cons = 0;
-      rc = window_to_sink(e, e->d_in, (u32)ss.h_fill, closing, closing && !ss.tail_running, sk, &cons);
+   while (off < n) {
+      pthread_mutex_lock(&a.mu);
+      while (!a.err && a.tail - a.head >= a.cap) pthread_cond_wait(&a.cv_space, &a.mu);
+      if (a.err) { rc = a.err; pthread_mutex_unlock(&a.mu); return rc; }
+      const size_t space = a.cap - (size_t)(a.tail - a.head);
+      const size_t take = (n - off < space) ? (n - off) : space;
+      const size_t pos = (size_t)(a.tail % a.cap);
+      pthread_mutex_unlock(&a.mu);
+      // [tail, tail + take) is not visible to the worker until tail moves
+      const size_t first = (take < a.cap - pos) ? take : a.cap - pos;
+      memcpy(e->h_in + pos, in + off, first);
+      if (take > first) memcpy(e->h_in, in + off + first, take - first);
+      pthread_mutex_lock(&a.mu);
+      a.tail += take;
+      e->ss.tail_running = (end_mode == 0);
+      e->ss.st.in_bytes += take;
+      pthread_cond_signal(&a.cv_work);
+      pthread_mutex_unlock(&a.mu);
+      off += take;
+      if ((rc = feed_drain(e, sink, user))) return rc;
+   }
+   if (end_mode != 0) {
+      pthread_mutex_lock(&a.mu);
+      a.pending_end = end_mode;
+      a.closing_done = false;
+      pthread_cond_signal(&a.cv_work);
+      while (!a.closing_done && !a.err) pthread_cond_wait(&a.cv_done, &a.mu);
+      a.pending_end = 0;
+      rc = a.err;
+      pthread_mutex_unlock(&a.mu);
       if (rc) return rc;
-      if (cons == 0 && !closing) return set_err(BZ2B200_EINTERNAL, "window made no progress");
-      if (cons < ss.h_fill) memmove(e->h_in, e->h_in + cons, ss.h_fill - cons);
-      ss.h_fill -= cons;
-      if (all_in && ss.h_fill == 0) break;
-      if (all_in && !closing) break;
    }
-   if (end_mode == 2) {
-      if ((rc = finish_stream(e, sk))) return rc;
-   }
-   return 0;
+   return feed_drain(e, sink, user);
 }
 
 int bz2b200_engine_set_stream(bz2b200_engine* h, void* cuda_stream)

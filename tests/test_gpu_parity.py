@@ -223,6 +223,64 @@ def test_flush_closes_block():
         pass
 
 
+def _stream_all(data, level, chunk, finish_with_last=True):
+    s = B.bzlib(level=level)
+    try:
+        n = len(data)
+        for i in range(0, n, chunk):
+            last = i + chunk >= n
+            if last and finish_with_last:
+                rc, used = s.call(data[i:i + chunk], binding.BZ_FINISH, out_chunk=1 << 20)
+                assert used == n - i
+                while rc == binding.BZ_FINISH_OK:
+                    rc, _ = s.call(b"", binding.BZ_FINISH, out_chunk=1 << 20)
+                assert rc == binding.BZ_STREAM_END
+            else:
+                rc, used = s.call(data[i:i + chunk], binding.BZ_RUN, out_chunk=1 << 20)
+                assert rc == binding.BZ_RUN_OK and used == len(data[i:i + chunk])
+        assert s.strm.total_in_lo32 == n & 0xFFFFFFFF and s.strm.total_out_lo32 == len(s.out)
+        return bytes(s.out)
+    finally:
+        s.end()
+
+
+def test_streaming_many_windows(engine_for, monkeypatch):
+    """The streaming feed is asynchronous (a worker cuts windows out of a pinned ring while the caller keeps
+    feeding): many small windows, chunk sizes that do not divide anything, ring wrap-around."""
+    lib = B.load()
+    d = S.gen_mixed(70_000_000, seg=1 << 22).tobytes()
+    exp = engine_for(1).compress(np.frombuffer(d, np.uint8))
+    monkeypatch.setenv("BZ2_B200_WINDOW_MB", "8")
+    lib.bz2b200_pool_clear()
+    try:
+        for chunk in (3_000_001, 64 << 20):
+            assert _stream_all(d, 1, chunk) == exp, chunk
+    finally:
+        monkeypatch.delenv("BZ2_B200_WINDOW_MB")
+        lib.bz2b200_pool_clear()
+
+
+def test_two_streams_on_two_threads(engine_for):
+    """Distinct bz_streams may be driven from different threads at the same time (threading)."""
+    import threading
+    datas = [S.gen_text(9_000_000, seed=21).tobytes(), S.gen_mixed(11_000_000, seg=1 << 20).tobytes()]
+    exps = [engine_for(9).compress(np.frombuffer(x, np.uint8)) for x in datas]
+    got, errs = [None, None], []
+
+    def work(k):
+        try:
+            got[k] = _stream_all(datas[k], 9, 1_000_003)
+        except Exception as ex:  # noqa: BLE001
+            errs.append(ex)
+    ths = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errs, errs
+    assert got[0] == exps[0] and got[1] == exps[1]
+
+
 def test_outbuff_full():
     lib = B.load()
     d = S.gen_random(50_000)
