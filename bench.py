@@ -47,7 +47,7 @@ def make_input(workload, n, rank=0):
     if workload == "runs":
         return S.gen_runs(n, seed=3 + rank)
     if workload == "mixed":
-        return S.gen_mixed(n, seg=64 << 20)
+        return S.gen_c4(n, seg=64 << 20)
     raise SystemExit(f"unknown workload {workload}")
 
 

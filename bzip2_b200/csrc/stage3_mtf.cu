@@ -138,9 +138,20 @@ __device__ __forceinline__ u32 run_digits(u32 r) { return 31 - __clz(r + 1); }
 // Also records the zero-run shape of the tile (lead / trail / inner symbol count) for RLE2.
 constexpr int MTF_CTA = 128;
 
+// move-to-front inside one list word: the entry in byte `bsel` leaves, the entries below it move up one byte,
+// `carry` (the entry pushed out of the previous word, or the symbol itself for word 0) enters at byte 0
+__device__ __forceinline__ u32 mtf_word_hit(u32 wv, u32 bsel, u32 carry)
+{
+   const u32 low = (1u << (8 * bsel)) - 1u;
+   return (wv & ~((low << 8) | 0xffu)) | ((wv & low) << 8) | carry;
+}
+
 __global__ void __launch_bounds__(MTF_CTA) k_mtf_encode(S3Params p)
 {
-   __shared__ u8 lst[256 * MTF_CTA];
+   // Column layout of 16-byte groups: one uint4 = sixteen consecutive list entries (entry i = byte i&3 of word
+   // (i>>2)&3 of group i>>4).  A lookup tests sixteen entries with four SIMD byte compares and the move-to-front
+   // shifts sixteen entries with four funnel shifts, so deep positions (binary data) cost ~1 instruction per entry.
+   __shared__ uint4 lst[16 * MTF_CTA];
    const u32 b = blockIdx.y;
    if (p.mode[b]) return;
    const u32 tid = threadIdx.x;
@@ -149,17 +160,13 @@ __global__ void __launch_bounds__(MTF_CTA) k_mtf_encode(S3Params p)
    const u32 ntile = (n + MTF_TILE - 1) / MTF_TILE;
    const u32 t0 = blockIdx.x * MTF_CTA;
    if (t0 >= ntile) return;
-   // stage the start lists of this CTA's tiles (coalesced 256-byte rows -> interleaved columns)
+   // stage the start lists of this CTA's tiles (coalesced 256-byte rows -> interleaved 16-byte columns)
    {
-      const u8* src = p.lists + ((size_t)b * p.tiles_max + t0) * 256;
+      const uint4* src = reinterpret_cast<const uint4*>(p.lists + ((size_t)b * p.tiles_max + t0) * 256);
       const u32 nt = min((u32)MTF_CTA, ntile - t0);
-      for (u32 q = tid; q < nt * 64; q += MTF_CTA) {
-         const u32 tile = q % nt, w = q / nt;       // lanes vary in tile: conflict-free shared-memory columns
-         const u32 v = reinterpret_cast<const u32*>(src)[tile * 64 + w];
-         lst[(w * 4 + 0) * MTF_CTA + tile] = (u8)v;
-         lst[(w * 4 + 1) * MTF_CTA + tile] = (u8)(v >> 8);
-         lst[(w * 4 + 2) * MTF_CTA + tile] = (u8)(v >> 16);
-         lst[(w * 4 + 3) * MTF_CTA + tile] = (u8)(v >> 24);
+      for (u32 q = tid; q < nt * 16; q += MTF_CTA) {
+         const u32 tile = q >> 4, g = q & 15;
+         lst[g * MTF_CTA + tile] = src[q];
       }
    }
    __syncthreads();
@@ -169,10 +176,8 @@ __global__ void __launch_bounds__(MTF_CTA) k_mtf_encode(S3Params p)
    const u32 a = start & 3u;
    const u32* in32 = reinterpret_cast<const u32*>(p.bwt + (start - a));
    u32* out32 = reinterpret_cast<u32*>(p.z + (start - a));
-   u8* my = lst + tid;
-   // the first four list entries live in registers (on BWT output most symbols hit one of them);
-   // shared-memory rows 4..255 hold the rest of the list, rows 0..3 are dead after this load
-   u32 l0 = my[0], l1 = my[MTF_CTA], l2 = my[2 * MTF_CTA], l3 = my[3 * MTF_CTA];
+   uint4* my = lst + tid;
+   uint4 G = my[0];                      // entries 0..15 live in registers; shared-memory row 0 is dead from here on
    u32 lead = 0, run = 0, inner = 0;
    bool seen_nz = false;
    const u32 nwords = (size + a + 3) >> 2;
@@ -184,26 +189,73 @@ __global__ void __launch_bounds__(MTF_CTA) k_mtf_encode(S3Params p)
          const i32 i = (i32)(w * 4 + k) - (i32)a;
          if (i < 0 || i >= (i32)size) continue;
          const u32 c = (word >> (8 * k)) & 0xff;
-         const bool e0 = (c == l0), e1 = (c == l1), e2 = (c == l2), e3 = (c == l3);
-         u32 pos = e0 ? 0u : e1 ? 1u : e2 ? 2u : 3u;
-         if (!(e0 | e1 | e2 | e3)) {
-            // deeper than the register window: shift rows 4..j-1 down by one while searching
-            u32 prev = l3;
-            u32 j = 4;
-            for (;;) {
-               const u32 cur = my[j * MTF_CTA];
-               my[j * MTF_CTA] = (u8)prev;
-               if (cur == c) break;
-               prev = cur;
-               j++;
+         const u32 cc = c * 0x01010101u;
+         u32 pos;
+         u32 hit = __vcmpeq4(G.x, cc);          // 0xff in every byte that equals c
+         if (hit) {
+            pos = (u32)(__ffs(hit) - 1) >> 3;
+            G.x = mtf_word_hit(G.x, pos, c);
+         } else {
+            const u32 h1 = __vcmpeq4(G.y, cc), h2 = __vcmpeq4(G.z, cc), h3 = __vcmpeq4(G.w, cc);
+            if (h1 | h2 | h3) {
+               const u32 c0 = G.x >> 24;
+               G.x = (G.x << 8) | c;
+               if (h1) { pos = 4 + ((u32)(__ffs(h1) - 1) >> 3); G.y = mtf_word_hit(G.y, pos - 4, c0); }
+               else {
+                  const u32 c1 = G.y >> 24;
+                  G.y = (G.y << 8) | c0;
+                  if (h2) { pos = 8 + ((u32)(__ffs(h2) - 1) >> 3); G.z = mtf_word_hit(G.z, pos - 8, c1); }
+                  else {
+                     const u32 c2 = G.z >> 24;
+                     G.z = (G.z << 8) | c1;
+                     pos = 12 + ((u32)(__ffs(h3) - 1) >> 3);
+                     G.w = mtf_word_hit(G.w, pos - 12, c2);
+                  }
+               }
+            } else {
+               // not among the first sixteen: shift the register group, then walk the shared-memory groups
+               u32 carry = G.w >> 24;
+               G.w = __funnelshift_l(G.z, G.w, 8);
+               G.z = __funnelshift_l(G.y, G.z, 8);
+               G.y = __funnelshift_l(G.x, G.y, 8);
+               G.x = (G.x << 8) | c;
+               u32 j = 1;
+               for (;;) {
+                  uint4 q = my[j * MTF_CTA];
+                  const u32 m0 = __vcmpeq4(q.x, cc), m1 = __vcmpeq4(q.y, cc), m2 = __vcmpeq4(q.z, cc), m3 = __vcmpeq4(q.w, cc);
+                  if (m0 | m1 | m2 | m3) {
+                     if (m0) { pos = (u32)(__ffs(m0) - 1) >> 3; q.x = mtf_word_hit(q.x, pos, carry); }
+                     else {
+                        const u32 d0 = q.x >> 24;
+                        q.x = (q.x << 8) | carry;
+                        if (m1) { pos = 4 + ((u32)(__ffs(m1) - 1) >> 3); q.y = mtf_word_hit(q.y, pos - 4, d0); }
+                        else {
+                           const u32 d1 = q.y >> 24;
+                           q.y = (q.y << 8) | d0;
+                           if (m2) { pos = 8 + ((u32)(__ffs(m2) - 1) >> 3); q.z = mtf_word_hit(q.z, pos - 8, d1); }
+                           else {
+                              const u32 d2 = q.z >> 24;
+                              q.z = (q.z << 8) | d1;
+                              pos = 12 + ((u32)(__ffs(m3) - 1) >> 3);
+                              q.w = mtf_word_hit(q.w, pos - 12, d2);
+                           }
+                        }
+                     }
+                     my[j * MTF_CTA] = q;
+                     pos += 16 * j;
+                     break;
+                  }
+                  const u32 out = q.w >> 24;
+                  q.w = __funnelshift_l(q.z, q.w, 8);
+                  q.z = __funnelshift_l(q.y, q.z, 8);
+                  q.y = __funnelshift_l(q.x, q.y, 8);
+                  q.x = (q.x << 8) | carry;
+                  my[j * MTF_CTA] = q;
+                  carry = out;
+                  j++;
+               }
             }
-            pos = j;
          }
-         // move-to-front inside the register window (a miss shifts the whole window, like a hit at 3)
-         l3 = (e0 | e1 | e2) ? l3 : l2;
-         l2 = (e0 | e1) ? l2 : l1;
-         l1 = e0 ? l1 : l0;
-         l0 = c;
          zword |= pos << (8 * k);
          if (pos == 0) run++;
          else {

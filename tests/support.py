@@ -264,3 +264,28 @@ def gen_mixed(n, seg=1 << 20):
         pos += m
         kinds += 1
     return out
+
+
+def gen_c4(n, seg=64 << 20):
+    """segments cycling T, B, R.  T = the C2 text generator (one continuing stream),
+    B = sample1.ref || sample2.ref (311,036 bytes of real binary, tests/golden/) tiled, R = raw xorshift64*
+    bytes (seed 2, one continuing stream)."""
+    nseg = (n + seg - 1) // seg
+    n_t = sum(min(seg, n - k * seg) for k in range(nseg) if k % 3 == 0)
+    n_r = sum(min(seg, n - k * seg) for k in range(nseg) if k % 3 == 2)
+    text = gen_text(max(n_t, 1), TEXT_SEED)
+    rnd = gen_random(max(n_r, 1), 2)
+    with open(os.path.join(GOLDEN, "sample1.ref"), "rb") as f1, open(os.path.join(GOLDEN, "sample2.ref"), "rb") as f2:
+        binary = np.frombuffer(f1.read() + f2.read(), np.uint8)
+    out = np.empty(n, np.uint8)
+    tp = rp = 0
+    for k in range(nseg):
+        pos = k * seg
+        m = min(seg, n - pos)
+        if k % 3 == 0:
+            out[pos:pos + m] = text[tp:tp + m]; tp += m
+        elif k % 3 == 1:
+            out[pos:pos + m] = np.resize(binary, m)
+        else:
+            out[pos:pos + m] = rnd[rp:rp + m]; rp += m
+    return out
