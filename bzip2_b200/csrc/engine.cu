@@ -135,6 +135,8 @@ static int engine_new(EngineFull** out, int device, int level, size_t window_byt
       e->s2_group = g ? (u32)atoi(g) : 0;
       const char* tf = getenv("BZ2_B200_TEXT_FIRST");
       e->text_first = tf ? (u32)atoi(tf) : 1;
+      const char* pe = getenv("BZ2_B200_PERIODIC");
+      e->periodic = pe ? (u32)atoi(pe) : 1;
       const char* r8 = getenv("BZ2_B200_RADIX_C8K");
       e->radix_c8k = r8 ? (u32)atoi(r8) : 1;
       const char* rx = getenv("BZ2_B200_RADIX_MIN");

@@ -112,6 +112,7 @@ struct Engine {
    u32 *kk, *nbins, *hh, *kbits, *ksym;   // [blk_cap]
    u64 *K, *kscrA, *kscrB; // [E] packed text keys; 64-bit key scratch of the large path
    u32 text_first;         // first refinement round sorts by text keys (default on)
+   u32 periodic;           // resolve tandem-repeat segments in one step (default on)
    u32 radix_c8k;          // 4097..8192: 1 = shared-memory radix CTA of 1024, 0 = the HBM radix path of the large class
    u32 radix_min;          // CTA sort classes with at least this many threads use radix passes (1024 = none)
    u32 kg_mode;            // k-gram bucket sort: 0 = count / rank / atomic scatter, 1 = count with arrival index / place

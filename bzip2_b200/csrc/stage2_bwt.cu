@@ -422,6 +422,7 @@ k_refine_medium(S2Params p, ListsDev Lout, const u64* items, u32 count, u32 roun
    const u32 pos = (u32)(entry >> 32);
    const u32 b = (u32)(entry >> 20) & 0xfffu;
    const u32 len = (u32)entry & 0xfffffu;
+   if (len == 0 && (WARP || vseg)) return;               // resolved by k_resolve_periodic (warp- resp. CTA-uniform)
    u32 xb = 0, n = 1, shift = 0, depth = 0;
    if (vseg) { xb = p.X[b]; n = p.X[b + 1] - xb; shift = round_shift(p, b, round, &depth); }
    u32 n2 = 64;
@@ -532,6 +533,7 @@ __global__ void __launch_bounds__(THREADS) k_refine_radix(S2Params p, ListsDev L
    const u32 pos = (u32)(entry >> 32);
    const u32 b = (u32)(entry >> 20) & 0xfffu;
    const u32 len = (u32)entry & 0xfffffu;
+   if (len == 0) return;                                  // resolved by k_resolve_periodic
    const u32 xb = p.X[b], n = p.X[b + 1] - xb;
    u32 depth;
    const u32 shift = round_shift(p, b, round, &depth);
@@ -695,6 +697,7 @@ __global__ void __launch_bounds__(LG_THREADS) k_refine_large(S2Params p, ListsDe
    const u32 pos = (u32)(entry >> 32);
    const u32 b = (u32)(entry >> 20) & 0xfffu;
    const u32 len = (u32)entry & 0xfffffu;
+   if (len == 0) return;                                  // resolved by k_resolve_periodic
    const u32 xb = p.X[b], n = p.X[b + 1] - xb;
    u32 depth;
    const u32 shift0 = round_shift(p, b, round, &depth);
@@ -836,6 +839,77 @@ __global__ void __launch_bounds__(LG_THREADS) k_refine_large(S2Params p, ListsDe
    }
 }
 
+// ---- 2d. tandem repeats ---------------------------------------------------------------------
+// A segment sorted to depth d whose members are the positions i, i+p, i+2p, ... (p <= d) needs no more
+// doubling: every member is  u . (next member)  with the same p-symbol prefix u, so their order is the order
+// of the chain ends.  Only the last member continues outside the segment (at X = max+p); if X ranks below
+// the segment the members sort by descending position, if above by ascending position (the tandem-repeat
+// rule of suffix sorters; divsufsort's tr_copy plays this role in the reference, blocksort.c:1040-1100).
+// Periodic inputs (the reference manual's worst case) otherwise cost log2(n/d) rounds over every element.
+// One CTA per listed segment; resolved segments get len = 0 in the worklist and the sort kernels skip them.
+constexpr int AP_THREADS = 256;
+
+__global__ void __launch_bounds__(AP_THREADS) k_resolve_periodic(S2Params p, u64* items, u32 count, u32 round)
+{
+   __shared__ u32 red_mn[AP_THREADS / 32], red_mx[AP_THREADS / 32];
+   __shared__ u32 s_bad;
+   const u32 seg = blockIdx.x;
+   if (seg >= count) return;
+   const u64 entry = items[seg];
+   const u32 pos = (u32)(entry >> 32);
+   const u32 b = (u32)(entry >> 20) & 0xfffu;
+   const u32 len = (u32)entry & 0xfffffu;
+   if (len < 3) return;
+   const u32 xb = p.X[b], n = p.X[b + 1] - xb;
+   u32 depth_after;
+   const u32 depth = round_shift(p, b, round, &depth_after);       // the segment's members share their first `depth` symbols
+   const u32 tag = round + 1;
+   const u32 t = threadIdx.x, w = t >> 5, l = lane_id();
+   // 1. min / max position
+   u32 mn = 0xffffffffu, mx = 0;
+   for (u32 i = t; i < len; i += AP_THREADS) { const u32 v = p.sa[pos + i]; mn = min(mn, v); mx = max(mx, v); }
+#pragma unroll
+   for (int d = 16; d > 0; d >>= 1) { mn = min(mn, __shfl_xor_sync(FULL, mn, d)); mx = max(mx, __shfl_xor_sync(FULL, mx, d)); }
+   if (l == 0) { red_mn[w] = mn; red_mx[w] = mx; }
+   if (t == 0) s_bad = 0;
+   __syncthreads();
+#pragma unroll
+   for (int k = 0; k < AP_THREADS / 32; k++) { mn = min(mn, red_mn[k]); mx = max(mx, red_mx[k]); }
+   const u32 span = mx - mn;
+   const u32 step = span / (len - 1);
+   if (p.debug && t == 0 && len > 8192) printf("[ap] round %u blk %u len %u mn %u mx %u step %u depth %u n %u\n", round, b, len, mn, mx, step, depth, n);
+   if (step == 0 || step * (len - 1) != span || step > depth) return;       // uniform over the CTA
+   u32 xpos = mx + step; if (xpos >= n) xpos -= n;
+   const u32 gs = pos - xb;
+   if (xpos == mn && (u64)step * len == n) {
+      // the progression closes on itself: the block is u^len with |u| = step <= depth, these len rotations are
+      // equal for good.  Record the multiplicity and retire the segment instead of doubling up to depth n.
+      for (u32 i = t; i < len; i += AP_THREADS) { const u32 v = p.sa[pos + i]; if ((v - mn) % step) s_bad = 1; }
+      __syncthreads();
+      if (!s_bad && t == 0) { atomicMax(&p.power_q[b], len); items[seg] = entry & ~(u64)0xfffffu; }
+      return;
+   }
+   // the continuation of the last member must lie outside the segment
+   const u32 xr = rk_read(p.rank[xb + xpos], tag);
+   if (xr >= gs && xr < gs + len) return;
+   const bool ascending = xr >= gs + len;
+   // 2. every member on the progression?  (members are distinct, so len multiples inside [mn, mx] are all of them)
+   for (u32 i = t; i < len; i += AP_THREADS) { const u32 v = p.sa[pos + i]; if ((v - mn) % step) s_bad = 1; }
+   __syncthreads();
+   if (s_bad) return;
+   // 3. final order and final ranks
+   for (u32 i = t; i < len; i += AP_THREADS) {
+      const u32 v = p.sa[pos + i];
+      const u32 k = (v - mn) / step;
+      const u32 r = ascending ? k : len - 1 - k;
+      p.idxB[pos + r] = v;
+      p.rank[xb + v] = rk_pack(tag, gs, gs + r);
+   }
+   __syncthreads();
+   for (u32 i = t; i < len; i += AP_THREADS) p.sa[pos + i] = p.idxB[pos + i];
+   if (t == 0) items[seg] = entry & ~(u64)0xfffffu;                          // done: nothing left to sort
+}
+
 // ---- 3. last column -------------------------------------------------------------------
 __global__ void __launch_bounds__(KG_THREADS) k_bwt_out(S2Params p, u8* bwt, u32* origptr)
 {
@@ -854,6 +928,56 @@ __global__ void __launch_bounds__(KG_THREADS) k_bwt_out(S2Params p, u8* bwt, u32
          bwt[xb + i] = T[s ? s - 1 : n - 1];
       }
    }
+}
+
+// origPtr on exact powers u^q: the reference's value is lo + g, g an artefact of divsufsort's internal order
+// (SURVEY 7#1).  For units with a single B* suffix -- one local-maximum run, cyclically: constant data after
+// RLE1, "aab"-like periods -- g depends on the parity of |u| and on q only (measured on the reference, pinned by
+// tests/golden/origptr_powers.json; the CPU statement is oracle/bz2_oracle.c orc_power_offset).  One warp per block.
+__global__ void __launch_bounds__(32) k_power_origptr(S2Params p, u32* origptr)
+{
+   const u32 b = p.b0 + blockIdx.x;
+   const u32 q = p.power_q[b];
+   if (q < 2) return;
+   const u32 xb = p.X[b], n = p.X[b + 1] - xb;
+   if (n % q) return;
+   const u32 per = n / q;
+   if (per == 1) return;                                   // all-equal block: origPtr stays 0
+   const u8* T = p.T + xb;
+   const u32 l = lane_id();
+   // every lane scans a contiguous chunk of the unit's step signs and summarises it as
+   // (first non-zero sign, last non-zero sign, number of +- transitions inside)
+   const u32 chunk = (per + 31) / 32;
+   const u32 lo = min(per, l * chunk), hi = min(per, lo + chunk);
+   int first = 0, last = 0; u32 cnt = 0;
+   for (u32 i = lo; i < hi; i++) {
+      const int a = T[i], c = T[(i + 1 == per) ? 0 : i + 1];
+      const int sgn = (c > a) - (c < a);
+      if (!sgn) continue;
+      if (!first) first = sgn;
+      if (last > 0 && sgn < 0) cnt++;
+      last = sgn;
+   }
+   // lane 0 stitches the 32 summaries in order, then across the wrap
+   u32 peaks = 0; int run_last = 0, run_first = 0;
+   for (int k = 0; k < 32; k++) {
+      const int f = __shfl_sync(FULL, first, k), la = __shfl_sync(FULL, last, k);
+      const u32 c = __shfl_sync(FULL, cnt, k);
+      peaks += c;
+      if (f) {
+         if (run_last > 0 && f < 0) peaks++;
+         if (!run_first) run_first = f;
+         run_last = la;
+      }
+   }
+   if (run_last > 0 && run_first < 0) peaks++;
+   if (l != 0 || peaks != 1) return;
+   u32 g;
+   if ((per & 1u) == 0 || q <= 9) g = 1;
+   else if (q <= 1025) g = (q & 1u) ? (q + 1) / 2 : 0;
+   else if (q <= 1027) g = 0;
+   else g = 513;
+   origptr[b] += g;
 }
 
 // --------------------------------------------------------------------------------------
@@ -932,7 +1056,7 @@ int stage2_run(Engine* e, u32 nb, u32 E)
    p.hist = e->hist; p.hist_stride = e->hist_stride; p.code = e->code; p.kk = e->kk; p.nbins = e->nbins;
    p.hh = e->hh; p.kbits = e->kbits; p.ksym = e->ksym; p.K = e->K; p.kscrA = e->kscrA; p.kscrB = e->kscrB;
    p.text_first = e->text_first;
-   p.debug = 0;
+   p.debug = trace_on() ? 1 : 0;
    p.blockmap = e->blockmap;
    p.power_q = e->bt.power_q; p.inuse = e->bt.inuse; p.ninuse = e->bt.ninuse;
 
@@ -1006,6 +1130,14 @@ int stage2_run(Engine* e, u32 nb, u32 E)
          const bool text = (round == 0) && e->text_first;
          // The size classes of one round touch disjoint segments, so they run side by side: the few
          // long-running CTAs of the large and CTA-sort classes overlap the sub-warp classes' tails.
+         // tandem repeats: the large class from round 0 on (few segments), every CTA/warp-sorted class from round 2 on
+         if (e->periodic) {
+            for (int c = (round >= 2 ? 0 : N_BIG_CLASSES - 1); c < N_BIG_CLASSES; c++) {
+               const u32 cn = cnt[N_SMALL_CLASSES + c];
+               if (cn) { k_resolve_periodic<<<cn, AP_THREADS, 0, st>>>(p, bi[c], cn, round); BZ_KCHECK(e); }
+            }
+            dbg_sync(e, "k_resolve_periodic");
+         }
          const bool fork = e->s2_streams && total > 64;
          cudaStream_t sL = st, sM = st, sW = st;
          if (fork) {
@@ -1048,6 +1180,7 @@ int stage2_run(Engine* e, u32 nb, u32 E)
          cur = nxt;
       }
       k_bwt_out<<<gtiles, KG_THREADS, 0, st>>>(p, e->bwt, e->bt.origptr);                       BZ_KCHECK(e);
+      k_power_origptr<<<g, 32, 0, st>>>(p, e->bt.origptr);                                      BZ_KCHECK(e);
    }
    return 0;
 }

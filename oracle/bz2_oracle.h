@@ -15,7 +15,9 @@
  * itself compiled as oracle/_ref/libbz2_ref.so (differential fuzz in
  * tests/test_oracle_vs_ref.py).  Known limit: on blocks that are an exact power
  * u^q (q >= 2) the reference's origPtr is an artefact of divsufsort's internal
- * order; see orc_bwt().
+ * order.  It is reproduced for units with a single B*
+ * suffix (constant data, "aab"-like periods; orc_power_offset()), not for units
+ * with several.
  */
 #ifndef BZ2_ORACLE_H
 #define BZ2_ORACLE_H
@@ -48,6 +50,10 @@ int32_t orc_rle1_emit(const uint8_t* in, uint64_t begin, uint64_t end,
  * q >= 2, *orig_ptr is the SMALLEST rank among the q equal copies (lo); the
  * reference's value is lo + g with g in [0,q). */
 int32_t orc_bwt(const uint8_t* blk, int32_t n, uint8_t* bwt, int32_t* orig_ptr);
+
+/* g of the reference's origPtr = lo + g on an exact power u^q whose unit has a single B* suffix (measured
+ * rule, see the definition); -1 when the unit has several B* suffixes (origPtr stays lo there). */
+int32_t orc_power_offset(const uint8_t* blk, int32_t n, int32_t q);
 
 /* MTF + zero-run coding (compress.c:93-229). Returns nMTF. */
 int32_t orc_mtf(const uint8_t* bwt, int32_t n, const uint8_t* in_use,

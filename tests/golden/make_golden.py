@@ -31,6 +31,7 @@ def stream_cases():
     yield "random_300k_L2", S.gen_random(300_000), 2
     yield "random_1M_L9", S.gen_random(1_000_000, seed=5), 9
     yield "period1000_1M_L9", S.gen_period1000(1_000_000), 9
+    yield from S.power_stream_cases()
     yield "period1000_500k_L1", S.gen_period1000(500_000), 1
     yield "aab_1M_L9", S.gen_tile(1_000_000, b"aab"), 9
     yield "runs_4M_L9", S.gen_runs(4_000_000), 9
@@ -47,8 +48,9 @@ def stream_cases():
 
 
 def power_cases():
-    units = [b"ab", b"ba", b"abc", b"aab", b"cab", b"abcabd", b"1234567", b"a", b"zyx", b"abab"]
-    qs = [2, 3, 8, 9, 10, 11, 12, 100, 1000, 1024, 1025, 2048, 2049, 5000]
+    units = [b"ab", b"ba", b"abc", b"aab", b"cab", b"abcabd", b"1234567", b"a", b"zyx", b"abab",
+             b"\x00\x00\x00\x00\xfb", b"\xff\xff\xff\xff\xfb", b"aabb", b"acb", b"abcdcb", b"qqzzq"]
+    qs = [2, 3, 8, 9, 10, 11, 12, 13, 100, 101, 1000, 1001, 1024, 1025, 1026, 1027, 1028, 2048, 2049, 5000]
     for u in units:
         for q in qs:
             if len(u) * q <= 60000:
@@ -72,7 +74,7 @@ def main():
     for u, q in power_cases():
         blk = np.frombuffer(u * q, np.uint8)
         _, op = S.ref_bwt(blk)
-        powers.append({"unit": u.decode(), "q": q, "orig_ptr": int(op)})
+        powers.append({"unit": u.decode("latin-1"), "q": q, "orig_ptr": int(op)})
     json.dump(powers, open(os.path.join(HERE, "origptr_powers.json"), "w"), indent=0)
     print(len(powers), "power cases")
 

@@ -45,6 +45,8 @@ def oracle():
     lib.orc_rle1_emit.argtypes = [u8p, C.c_uint64, C.c_uint64, u8p, u8p]
     lib.orc_bwt.restype = C.c_int32
     lib.orc_bwt.argtypes = [u8p, C.c_int32, u8p, C.POINTER(C.c_int32)]
+    lib.orc_power_offset.restype = C.c_int32
+    lib.orc_power_offset.argtypes = [u8p, C.c_int32, C.c_int32]
     lib.orc_mtf.restype = C.c_int32
     lib.orc_mtf.argtypes = [u8p, C.c_int32, u8p, C.POINTER(C.c_uint16), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.orc_make_code_lengths.restype = None
@@ -172,6 +174,12 @@ def orc_bwt(block):
     return out, op.value, q
 
 
+def orc_power_offset(block, q):
+    """g with origPtr_ref = lo + g for an exact power block (single-B* units), or -1."""
+    a = as_u8(block)
+    return int(oracle().orc_power_offset(_buf(a), a.size, q))
+
+
 def orc_mtf(bwt, inuse):
     a = as_u8(bwt)
     iu = as_u8(inuse)
@@ -289,3 +297,13 @@ def gen_c4(n, seg=64 << 20):
         else:
             out[pos:pos + m] = rnd[rp:rp + m]; rp += m
     return out
+
+
+def power_stream_cases():
+    """Inputs whose blocks are exact powers of a unit with a single B* suffix (golden streams minted from the reference)."""
+    yield "zeros_2M_L9", np.zeros(2_000_000, np.uint8), 9
+    yield "zeros_700k_L1", np.zeros(700_000, np.uint8), 1
+    yield "ff_1M_L5", np.full(1_000_000, 255, np.uint8), 5
+    yield "aab_2M_L9", gen_tile(2_000_000, b"aab"), 9
+    yield "aab_500k_L1", gen_tile(500_000, b"aab"), 1
+    yield "period7_400k_L1", gen_tile(400_000, b"1234567"), 1

@@ -148,10 +148,14 @@ def test_all_levels(engine_for):
 
 
 def test_exact_power_blocks_bwt(engine_for):
-    """Equal rotations: BWT bytes are canonical, the block is flagged with its multiplicity q, and
-    origPtr lies in the tie group.  (The reference's pick inside the group is checked separately.)"""
+    """Equal rotations: BWT bytes are canonical, the block is flagged with its multiplicity q, and origPtr lies
+    in the tie group -- at the reference's own position inside it when the unit has a single B* suffix."""
     eng = engine_for(9)
-    for unit, q in ((b"ab", 1000), (b"abc", 5000), (b"abcabd", 2049), (b"x", 70000), (b"cab", 33327)):
+    gold = {(g["unit"], g["q"]): g["orig_ptr"] for g in json.load(open(os.path.join(G, "origptr_powers.json")))}
+    cases = [(b"ab", 1000), (b"abc", 5000), (b"abcabd", 2049), (b"x", 70000), (b"cab", 33327), (b"aab", 1027), (b"aab", 1028),
+             (b"aab", 13), (b"1234567", 1001), (b"ba", 9), (b"acb", 1026), (b"qqzzq", 100), (b"abc", 299993), (b"abcdcb", 5000)]
+    exact = 0
+    for unit, q in cases:
         d = np.frombuffer(unit * q, np.uint8)
         out = eng.compress(d)
         assert bz2.decompress(out) == d.tobytes()
@@ -160,7 +164,33 @@ def test_exact_power_blocks_bwt(engine_for):
         n = len(enc)
         assert np.array_equal(eng.fetch("bwt", np.uint8)[:n], bw)
         assert int(eng.fetch("power_q", np.uint32)[0]) == (qq if qq > 1 else 0)
-        assert lo <= int(eng.fetch("origptr", np.uint32)[0]) < lo + qq
+        op = int(eng.fetch("origptr", np.uint32)[0])
+        assert lo <= op < lo + qq
+        off = S.orc_power_offset(enc, qq)
+        if off >= 0:
+            assert op == lo + off, (unit, q)
+            if (unit.decode("latin-1"), q) in gold and len(enc) == len(d):
+                assert op == gold[(unit.decode("latin-1"), q)], (unit, q)
+                exact += 1
+    assert exact >= 8
+
+
+def test_periodic_segments_resolve_in_one_step(engine_for):
+    """Tandem-repeat segments (k_resolve_periodic) and early exact-power detection: same bytes as the oracle, and far
+    fewer doubling rounds than log2(n / depth)."""
+    for name, data, level in S.power_stream_cases():
+        eng = engine_for(level)
+        out = eng.compress(S.as_u8(data))
+        assert out == S.orc_compress(data, level), name
+    eng = engine_for(9)
+    d = S.gen_tile(3_000_000, b"aab")
+    out = eng.compress(d)
+    assert out == S.orc_compress(d, 9)
+    assert eng.stats.bwt_rounds <= 4
+    d = S.gen_period1000(2_000_000)
+    out = eng.compress(d)
+    assert out == S.orc_compress(d, 9)
+    assert eng.stats.bwt_rounds <= 12
 
 
 # ------------------------------------------------------------------ libbz2 streaming API behaviour (bzlib.c:400-454)

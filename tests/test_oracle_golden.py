@@ -48,14 +48,28 @@ def test_power_block_bwt_and_period():
     """Exact powers: the oracle's BWT bytes are canonical and it reports q; the reference's origPtr
     (golden) always lies inside the tie group [lo, lo+q)."""
     gold = json.load(open(os.path.join(G, "origptr_powers.json")))
+    checked = 0
     for g in gold:
         if len(g["unit"]) * g["q"] > 70000:
             continue
-        blk = np.frombuffer(g["unit"].encode() * g["q"], np.uint8)
+        blk = np.frombuffer(g["unit"].encode("latin-1") * g["q"], np.uint8)
         _, lo, q = S.orc_bwt(blk)
         # q reported is the full multiplicity (e.g. "abab"^3 = "ab"^6)
         assert q >= g["q"] and q % g["q"] == 0
         assert lo <= g["orig_ptr"] < lo + q, g
+        off = S.orc_power_offset(blk, q)
+        if off >= 0:                       # unit with a single B* suffix: the reference's choice is reproduced
+            assert lo + off == g["orig_ptr"], g
+            checked += 1
+    assert checked >= 100
+
+
+def test_power_streams_match_reference_bytes():
+    """Whole streams over exact-power blocks with single-B* units (constant data, "aab") are byte-identical."""
+    gold = json.load(open(os.path.join(G, "streams.json")))
+    for name, data, level in S.power_stream_cases():
+        out = S.orc_compress(data, level)
+        assert hashlib.sha256(out).hexdigest() == gold[name]["sha256"], name
 
 
 def test_rle1_split_rules():

@@ -67,3 +67,37 @@ def test_tail_merge_corner():
     assert len(S.ref_trace(d, 1)[0]) == 1
     assert S.ref_compress(d, 1) == S.orc_compress(d, 1)
     assert len(S.orc_split(d, 1, tail_merge=0)) == 2
+
+
+def test_power_offset_rule_against_reference():
+    """Exact powers of units with one B* suffix: lo + orc_power_offset == the reference's origPtr."""
+    import random
+    rng = random.Random(77)
+    done = 0
+    while done < 120:
+        k = rng.randint(2, 9)
+        vals = sorted(rng.sample(range(256), k))
+        up = []
+        for v in vals:
+            up += [v] * rng.choice([1, 1, 2, 5])
+        down = []
+        for v in reversed(vals[1:-1]):
+            if rng.random() < 0.6:
+                down += [v] * rng.choice([1, 2])
+        u = bytes(up + down)
+        r = rng.randrange(len(u))
+        u = u[r:] + u[:r]
+        p = len(u)
+        if any(p % d == 0 and u == u[:d] * (p // d) for d in range(1, p)):
+            continue
+        q = rng.choice([2, 5, 9, 10, 11, 64, 65, 1024, 1025, 1026, 1027, 1028, 3000, rng.randint(2, 2000)])
+        if p * q > 200_000:
+            continue
+        blk = np.frombuffer(u * q, np.uint8)
+        off = S.orc_power_offset(blk, q)
+        if off < 0:
+            continue                                    # several B* suffixes: outside the rule
+        _, lo, qq = S.orc_bwt(blk)
+        _, op = S.ref_bwt(blk)
+        assert qq == q and lo + off == op, (u, q, lo, off, op)
+        done += 1
