@@ -849,12 +849,17 @@ __global__ void __launch_bounds__(LG_THREADS) k_refine_large(S2Params p, ListsDe
 // One CTA per listed segment; resolved segments get len = 0 in the worklist and the sort kernels skip them.
 constexpr int AP_THREADS = 256;
 
-__global__ void __launch_bounds__(AP_THREADS) k_resolve_periodic(S2Params p, u64* items, u32 count, u32 round)
+struct ApLists { u64* items[N_BIG_CLASSES]; u32 start[N_BIG_CLASSES + 1]; };   // the worklists of one round, concatenated
+
+__global__ void __launch_bounds__(AP_THREADS) k_resolve_periodic(S2Params p, ApLists L, u32 round)
 {
    __shared__ u32 red_mn[AP_THREADS / 32], red_mx[AP_THREADS / 32];
    __shared__ u32 s_bad;
-   const u32 seg = blockIdx.x;
-   if (seg >= count) return;
+   int cls = 0;
+#pragma unroll
+   for (int c = 1; c < N_BIG_CLASSES; c++) if (blockIdx.x >= L.start[c]) cls = c;
+   u64* const items = L.items[cls];
+   const u32 seg = blockIdx.x - L.start[cls];
    const u64 entry = items[seg];
    const u32 pos = (u32)(entry >> 32);
    const u32 b = (u32)(entry >> 20) & 0xfffu;
@@ -1132,10 +1137,15 @@ int stage2_run(Engine* e, u32 nb, u32 E)
          // long-running CTAs of the large and CTA-sort classes overlap the sub-warp classes' tails.
          // tandem repeats: the large class from round 0 on (few segments), every CTA/warp-sorted class from round 2 on
          if (e->periodic) {
-            for (int c = (round >= 2 ? 0 : N_BIG_CLASSES - 1); c < N_BIG_CLASSES; c++) {
-               const u32 cn = cnt[N_SMALL_CLASSES + c];
-               if (cn) { k_resolve_periodic<<<cn, AP_THREADS, 0, st>>>(p, bi[c], cn, round); BZ_KCHECK(e); }
+            ApLists AL;
+            u32 tot = 0;
+            for (int c = 0; c < N_BIG_CLASSES; c++) {
+               AL.items[c] = bi[c];
+               AL.start[c] = tot;
+               if (round >= 2 || c == N_BIG_CLASSES - 1) tot += cnt[N_SMALL_CLASSES + c];
             }
+            AL.start[N_BIG_CLASSES] = tot;
+            if (tot) { k_resolve_periodic<<<tot, AP_THREADS, 0, st>>>(p, AL, round); BZ_KCHECK(e); }
             dbg_sync(e, "k_resolve_periodic");
          }
          const bool fork = e->s2_streams && total > 64;

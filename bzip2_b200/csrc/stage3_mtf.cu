@@ -5,7 +5,7 @@
 //   k_mtf_summary  (warp/tile)  distinct symbols of the tile, most recent first.  The
 //                               effect of a tile on the MTF list is "move these to the
 //                               front in this order", which composes left to right.
-//   k_mtf_lists    (CTA/block)  folds the summaries, storing the list each tile starts with
+//   k_mtf_lists    (warp/block) folds the summaries, storing the list each tile starts with
 //   k_mtf_encode   (thread/tile) the real MTF with the tile's list in shared memory (column
 //                               layout, one column per thread); 32 tiles advance per warp
 //                               instruction.  Also records the tile's zero-run shape.
@@ -70,63 +70,100 @@ __global__ void __launch_bounds__(256) k_mtf_summary(S3Params p)
    if (l == 0) p.tilecnt[(size_t)b * p.tiles_max + t] = count;
 }
 
-__global__ void __launch_bounds__(256) k_mtf_lists(S3Params p)
+// One WARP per block folds the tile summaries in order and stores the list every tile starts with.  Lane l
+// holds list entries 8l..8l+7; the tile's symbol set is a 256-byte membership row in shared memory; the
+// survivors are compacted behind the tile's own recency order through a 256-byte shared-memory row.  Only
+// warp-level synchronisation per tile (the CTA-wide version needed four barriers per tile and ran 879 of them
+// back to back at 12 % occupancy).
+constexpr int ML_WARPS = 4;
+__global__ void __launch_bounds__(ML_WARPS * 32) k_mtf_lists(S3Params p, u32 nb)
 {
-   __shared__ u8 cur[2][256];
-   __shared__ u8 inset[256];
-   __shared__ u32 wcnt[8];
-   const u32 b = blockIdx.x;
-   const u32 tid = threadIdx.x, w = tid >> 5, l = lane_id();
+   __shared__ __align__(8) u8 row[ML_WARPS][256];
+   __shared__ __align__(8) u8 inset[ML_WARPS][256];
+   const u32 w = threadIdx.x >> 5, l = lane_id();
+   const u32 b = blockIdx.x * ML_WARPS + w;
+   if (b >= nb) return;
+   u8* const in = inset[w];
    const u32 n = p.X[b + 1] - p.X[b];
    const u32 ntile = (n + MTF_TILE - 1) / MTF_TILE;
-   cur[0][tid] = 0; cur[1][tid] = 0;
-   const bool used = p.inuse[(size_t)b * 256 + tid] != 0;
-   {
-      const u32 bal = __ballot_sync(FULL, used);
-      if (l == 0) wcnt[w] = __popc(bal);
-      __syncthreads();
-      u32 base = 0;
-      for (u32 k = 0; k < w; k++) base += wcnt[k];
-      if (used) cur[0][base + __popc(bal & lanemask_lt())] = (u8)tid;
-   }
    const u32 nu = p.ninuse[b];
-   __syncthreads();
+   u8* const my = row[w];
+   // initial list: the in-use byte values in ascending order (compress.c:124-129), zero padded
+   {
+      u32 cntl = 0;
+      u8 used[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) { used[k] = p.inuse[(size_t)b * 256 + l * 8 + k]; cntl += used[k] ? 1u : 0u; }
+      u32 base = warp_incl_sum(cntl) - cntl;
+      reinterpret_cast<uint2*>(my)[l] = make_uint2(0u, 0u);
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 8; k++) if (used[k]) my[base++] = (u8)(l * 8 + k);
+      __syncwarp();
+   }
+   uint2 cur = reinterpret_cast<const uint2*>(my)[l];
    u8* slot = p.lists + (size_t)b * p.tiles_max * 256;
    const u32* tc = p.tilecnt + (size_t)b * p.tiles_max;
    {
       // mean number of distinct symbols per tile is a proxy for the mean MTF position
       u32 sum = 0;
-      for (u32 t = tid; t < ntile; t += 256) sum += tc[t];
+      for (u32 t = l; t < ntile; t += 32) sum += tc[t];
       sum = warp_sum(sum);
-      __syncthreads();
-      if (l == 0) wcnt[w] = sum;
-      __syncthreads();
-      if (tid == 0) { u32 tot = 0; for (u32 k = 0; k < 8; k++) tot += wcnt[k]; p.mode[b] = (tot > p.warp_threshold * ntile) ? 1u : 0u; }
-      __syncthreads();
+      if (l == 0) p.mode[b] = (sum > p.warp_threshold * ntile) ? 1u : 0u;
    }
-   int sel = 0;
-   u8 pre_sym = slot[tid];
-   u32 pre_cnt = tc[0];
-   for (u32 t = 0; t < ntile; t++) {
-      const u8 s = pre_sym;
-      const u32 cnt = pre_cnt;
-      if (t + 1 < ntile) { pre_sym = slot[(size_t)(t + 1) * 256 + tid]; pre_cnt = tc[t + 1]; }
-      const u8 c = cur[sel][tid];
-      slot[(size_t)t * 256 + tid] = c;
-      inset[tid] = 0;
-      __syncthreads();
-      if (tid < cnt) inset[s] = 1;
-      __syncthreads();
-      const bool keep = (tid < nu) && !inset[c];
-      const u32 bal = __ballot_sync(FULL, keep);
-      if (l == 0) wcnt[w] = __popc(bal);
-      __syncthreads();
-      u32 base = cnt;
-      for (u32 k = 0; k < w; k++) base += wcnt[k];
-      if (keep) cur[sel ^ 1][base + __popc(bal & lanemask_lt())] = c;
-      if (tid < cnt) cur[sel ^ 1][tid] = s;
-      __syncthreads();
-      sel ^= 1;
+   // the fold is a dependent chain; the summaries it consumes are fetched a group of four tiles ahead so that
+   // no step waits on HBM
+   constexpr int PF = 4;
+   uint2 cs[PF]; u32 cc[PF];
+#pragma unroll
+   for (int j = 0; j < PF; j++) {
+      cs[j] = make_uint2(0u, 0u); cc[j] = 0;
+      if ((u32)j < ntile) { cs[j] = reinterpret_cast<const uint2*>(slot + (size_t)j * 256)[l]; cc[j] = tc[j]; }
+   }
+   for (u32 t0 = 0; t0 < ntile; t0 += PF) {
+      uint2 ns[PF]; u32 nc[PF];
+#pragma unroll
+      for (int j = 0; j < PF; j++) {
+         ns[j] = make_uint2(0u, 0u); nc[j] = 0;
+         const u32 tn = t0 + PF + (u32)j;
+         if (tn < ntile) { ns[j] = reinterpret_cast<const uint2*>(slot + (size_t)tn * 256)[l]; nc[j] = tc[tn]; }
+      }
+#pragma unroll
+      for (int j = 0; j < PF; j++) {
+         const u32 t = t0 + (u32)j;
+         if (t >= ntile) break;
+         const uint2 sy = cs[j];                       // the tile's distinct symbols, most recent first (cnt of them)
+         const u32 cnt = cc[j];
+         reinterpret_cast<uint2*>(slot + (size_t)t * 256)[l] = cur;     // the list this tile starts with
+         // membership table of the tile's symbols (one byte per value, this warp's row)
+         u32 sym[8];
+#pragma unroll
+         for (int k = 0; k < 8; k++) sym[k] = ((k < 4 ? sy.x : sy.y) >> (8 * (k & 3))) & 0xff;
+         reinterpret_cast<uint2*>(in)[l] = make_uint2(0u, 0u);
+         __syncwarp();
+#pragma unroll
+         for (int k = 0; k < 8; k++) if (l * 8 + k < cnt) in[sym[k]] = 1;
+         __syncwarp();
+         // survivors of the old list keep their order behind the tile's symbols
+         u32 keepm = 0, nk = 0;
+         u32 c[8];
+#pragma unroll
+         for (int k = 0; k < 8; k++) {
+            c[k] = ((k < 4 ? cur.x : cur.y) >> (8 * (k & 3))) & 0xff;
+            const bool keep = (l * 8 + k < nu) && !in[c[k]];
+            if (keep) { keepm |= 1u << k; nk++; }
+         }
+         u32 dst = cnt + warp_incl_sum(nk) - nk;
+         __syncwarp();
+#pragma unroll
+         for (int k = 0; k < 8; k++) if ((keepm >> k) & 1u) my[dst++] = (u8)c[k];
+#pragma unroll
+         for (int k = 0; k < 8; k++) if (l * 8 + k < cnt) my[l * 8 + k] = (u8)sym[k];
+         __syncwarp();
+         cur = reinterpret_cast<const uint2*>(my)[l];
+      }
+#pragma unroll
+      for (int j = 0; j < PF; j++) { cs[j] = ns[j]; cc[j] = nc[j]; }
    }
 }
 
@@ -487,7 +524,7 @@ int stage3_run(Engine* e, u32 nb, u32 E)
    const dim3 gw((tiles_max + 7) / 8, nb);
    const dim3 gt((tiles_max + 127) / 128, nb);
    k_mtf_summary<<<gw, 256, 0, st>>>(p);                BZ_KCHECK(e);
-   k_mtf_lists<<<nb, 256, 0, st>>>(p);                  BZ_KCHECK(e);
+   k_mtf_lists<<<(nb + ML_WARPS - 1) / ML_WARPS, ML_WARPS * 32, 0, st>>>(p, nb);   BZ_KCHECK(e);
    k_mtf_encode<<<gt, MTF_CTA, 0, st>>>(p);             BZ_KCHECK(e);
    k_mtf_encode_warp<<<gw, 256, 0, st>>>(p);            BZ_KCHECK(e);
    k_rle2_scan<<<(nb + 7) / 8, 256, 0, st>>>(p, nb);    BZ_KCHECK(e);
