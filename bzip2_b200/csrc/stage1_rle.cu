@@ -24,6 +24,7 @@ namespace bz {
 constexpr int S1_THREADS = 256;
 constexpr int S1_BPT = 16;
 constexpr int S1_TILE = S1_THREADS * S1_BPT;   // 4096
+constexpr int S1_STAGE = S1_TILE + S1_TILE / 4 + 48;   // worst case 5 output bytes per 4 input bytes, + alignment slack
 
 enum { S1_AGG = 0, S1_COUNT = 1, S1_SCATTER = 2, S1_FIND = 3, S1_LOCATE = 4 };
 
@@ -175,7 +176,35 @@ __global__ void __launch_bounds__(S1_THREADS) k_tile(S1Params p)
       if (threadIdx.x == 0) p.tile_size[tile] = ttotal;
       return;
    }
-   u32 E = p.tile_base[tile] + off;
+   if (MODE == S1_FIND || MODE == S1_LOCATE) {
+      u32 E = p.tile_base[tile] + off;
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+         if (ph[k] == 0xffff) continue;
+         const u32 jj = ph[k];
+         const i64 q = pos0 + k;
+         if (MODE == S1_FIND) { if (jj == 0 && E == findX) p.P[blockIdx.x + 1] = (u32)q; }
+         else if ((u32)q == locQ) p.EQ[blockIdx.x] = E;
+         E += (jj < 3) ? 1u : (jj == 3 ? 2u : 0u);
+      }
+      return;
+   }
+   // SCATTER.  The tile's output bytes and chunk-end flags are staged in shared memory at the alignment they
+   // have in HBM and flushed with 16-byte stores: byte stores straight to HBM cost one sector write each.
+   // One output byte of a tile can be "open": the count byte of a run that crosses the tile's end is written
+   // by the later tile in which the run (or its 255-byte chunk) ends, so the flush leaves it alone.
+   __shared__ __align__(16) u8 s_enc[S1_STAGE];
+   __shared__ __align__(16) u8 s_cend[S1_STAGE];
+   __shared__ int s_open;
+   const bool wr = (p.enc != nullptr);                     // shard scans only need the chunk-end flags
+   const u32 tb = p.tile_base[tile];
+   const u32 mis = tb & 15u;
+   const u32 nst = mis + ttotal;                           // staged bytes [mis, nst) belong to this tile
+   for (u32 g = threadIdx.x; g * 16 < nst + 16; g += S1_THREADS) reinterpret_cast<uint4*>(s_cend)[g] = make_uint4(0u, 0u, 0u, 0u);
+   if (threadIdx.x == 0) s_open = -1;
+   __syncthreads();
+   const i64 tile_last = min((i64)(tile + 1) * S1_TILE - (i64)align, (i64)p.W) - 1;
+   u32 El = off;                                           // offset inside the tile's output
 #pragma unroll
    for (int k = 0; k < 16; k++) {
       if (ph[k] == 0xffff) continue;
@@ -186,29 +215,48 @@ __global__ void __launch_bounds__(S1_THREADS) k_tile(S1Params p)
       bool last = (jj == 254);
       if (q == (i64)p.W - 1) last = last || (p.is_final != 0);
       else last = last || (nb_ != ch);
-      if (MODE == S1_FIND) {
-         if (jj == 0 && E == findX) p.P[blockIdx.x + 1] = (u32)q;
-         E += (jj < 3) ? 1u : (jj == 3 ? 2u : 0u);
-         continue;
+      if (q == tile_last && !last && jj >= 3) {
+         const int slot = (jj == 3) ? (int)El + 1 : (int)El - 1;
+         if (slot >= 0) s_open = slot;
       }
-      if (MODE == S1_LOCATE) {
-         if ((u32)q == locQ) p.EQ[blockIdx.x] = E;
-         E += (jj < 3) ? 1u : (jj == 3 ? 2u : 0u);
-         continue;
-      }
-      const bool wr = (p.enc != nullptr);                  // shard scans only need the chunk-end flags
       if (jj < 3) {
-         if (wr) p.enc[E] = (u8)ch;
-         if (last) p.cend[E] = 1;
-         E += 1;
+         s_enc[mis + El] = (u8)ch;
+         if (last) s_cend[mis + El] = 1;
+         El += 1;
       } else if (jj == 3) {
-         if (wr) p.enc[E] = (u8)ch;
-         if (last) { if (wr) p.enc[E + 1] = 0; p.cend[E + 1] = 1; }
-         E += 2;
-      } else if (E > 0) {
-         // E == 0 only in a shard scan that starts inside a run past its fourth byte: that chunk's count
-         // byte belongs to the previous shard's encoding, and no block can start before offset 0 here
-         if (last) { if (wr) p.enc[E - 1] = (u8)(jj - 3); p.cend[E - 1] = 1; }
+         s_enc[mis + El] = (u8)ch;
+         if (last) { s_enc[mis + El + 1] = 0; s_cend[mis + El + 1] = 1; }
+         El += 2;
+      } else if (last) {
+         if (El > 0) { s_enc[mis + El - 1] = (u8)(jj - 3); s_cend[mis + El - 1] = 1; }
+         else if (tb > 0) {
+            // the count byte lives in an earlier tile's output (that tile left it open).  tb == 0 only in a shard
+            // scan that starts inside a run past its fourth byte: the byte belongs to the previous shard's
+            // encoding, and no block can start before offset 0 here
+            if (wr) p.enc[tb - 1] = (u8)(jj - 3);
+            p.cend[tb - 1] = 1;
+         }
+      }
+   }
+   __syncthreads();
+   {
+      const int open = s_open >= 0 ? (int)mis + s_open : -1;
+      u8* const gc = p.cend + (tb - mis);
+      u8* const ge = wr ? p.enc + (tb - mis) : nullptr;
+      for (u32 g = threadIdx.x; g * 16 < nst; g += S1_THREADS) {
+         const u32 s0 = g * 16;
+         const u32 lo = max(s0, mis), hi = min(s0 + 16, nst);
+         const bool full = (lo == s0) && (hi == s0 + 16) && !(open >= (int)s0 && open < (int)s0 + 16);
+         if (full) {
+            *reinterpret_cast<uint4*>(gc + s0) = *reinterpret_cast<const uint4*>(s_cend + s0);
+            if (wr) *reinterpret_cast<uint4*>(ge + s0) = *reinterpret_cast<const uint4*>(s_enc + s0);
+         } else {
+            for (u32 x = lo; x < hi; x++) {
+               if ((int)x == open) continue;
+               gc[x] = s_cend[x];
+               if (wr) ge[x] = s_enc[x];
+            }
+         }
       }
    }
 }
