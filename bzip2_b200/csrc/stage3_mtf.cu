@@ -463,9 +463,29 @@ __global__ void __launch_bounds__(128) k_rle2_emit(S3Params p)
       const u32 start = xb + t * MTF_TILE;
       const u32 size = min((u32)MTF_TILE, n - t * MTF_TILE);
       const u32* m = p.tmeta + ((size_t)b * p.tiles_max + t) * 4;
-      u16* out = p.mtfv + (size_t)xb + b + m[3];
+      // symbols are gathered four at a time and stored as one aligned 64-bit word: a thread's 16-bit stores land
+      // in 32 different sectors per warp instruction otherwise.  Slots of a boundary word that belong to the
+      // neighbouring tile are never touched.
+      const size_t base = (size_t)xb + b + m[3];             // this tile's first slot in mtfv
+      u16* const mt = p.mtfv;
+      u64 acc = 0;
       u32 run = p.tcarry[(size_t)b * p.tiles_max + t];
       u32 o = 0;
+      auto put = [&](u32 sym) {
+         const size_t gi = base + o;
+         const u32 slot = (u32)gi & 3u;
+         acc |= (u64)sym << (16 * slot);
+         o++;
+         if (slot == 3) {
+            const size_t g0 = gi - 3;
+            if (g0 >= base) *reinterpret_cast<u64*>(mt + g0) = acc;
+            else {
+#pragma unroll
+               for (int j = 0; j < 4; j++) if (g0 + j >= base) mt[g0 + j] = (u16)(acc >> (16 * j));
+            }
+            acc = 0;
+         }
+      };
       u32 c0 = 0, c1 = 0, c2 = 0, c3 = 0;          // the hottest symbols are counted in registers
       // the tile is read as aligned 32-bit words (all tiles of a block share the misalignment)
       const u32 a = start & 3u;
@@ -481,21 +501,28 @@ __global__ void __launch_bounds__(128) k_rle2_emit(S3Params p)
             if (v == 0) { run++; continue; }
             if (run) {
                u32 zz = run - 1;
-               for (;;) { const u32 s = zz & 1; out[o++] = (u16)s; if (s) c1++; else c0++; if (zz < 2) break; zz = (zz - 2) >> 1; }
+               for (;;) { const u32 s = zz & 1; put(s); if (s) c1++; else c0++; if (zz < 2) break; zz = (zz - 2) >> 1; }
                run = 0;
             }
-            out[o++] = (u16)(v + 1);
+            put(v + 1);
             if (v == 1) c2++; else if (v == 2) c3++; else atomicAdd(&hist[v + 1], 1u);
          }
       }
       if (t == ntile - 1) {
          if (run) {
             u32 zz = run - 1;
-            for (;;) { const u32 s = zz & 1; out[o++] = (u16)s; if (s) c1++; else c0++; if (zz < 2) break; zz = (zz - 2) >> 1; }
+            for (;;) { const u32 s = zz & 1; put(s); if (s) c1++; else c0++; if (zz < 2) break; zz = (zz - 2) >> 1; }
          }
          const u32 eob = p.ninuse[b] + 1;
-         out[o++] = (u16)eob;
+         put(eob);
          atomicAdd(&hist[eob], 1u);
+      }
+      {
+         // the unfinished word
+         const size_t gi = base + o;
+         const u32 slot = (u32)gi & 3u;
+         const size_t g0 = gi - slot;
+         for (u32 j = 0; j < slot; j++) if (g0 + j >= base) mt[g0 + j] = (u16)(acc >> (16 * j));
       }
       if (c0) atomicAdd(&hist[0], c0);
       if (c1) atomicAdd(&hist[1], c1);
