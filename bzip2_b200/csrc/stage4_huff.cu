@@ -139,8 +139,12 @@ __global__ void __launch_bounds__(SEL_THREADS) k_huff_select(S4Params p)
 // ---- code lengths (huffman.c:63-148): one warp per (block, table), heap driven by lane 0 ----
 __global__ void __launch_bounds__(192) k_huff_lengths(S4Params p)
 {
-   __shared__ i32 s_heap[6][260];
-   __shared__ i32 s_w[6][516];
+   // BZ2_hbMakeCodeLengths (huffman.c:63-148) replayed literally -- the merge order under ties is part of the
+   // format's de-facto definition.  The heap holds (weight << 32 | node) words so that a sift step is one
+   // shared-memory load instead of the reference's weight[heap[y]] double indirection (the whole kernel is
+   // one dependent chain per table, so its run time is that chain's latency).
+   __shared__ u64 s_hp[6][260];
+   __shared__ i32 s_w[6][260];
    __shared__ i32 s_par[6][516];
    const u32 b = blockIdx.x;
    const u32 t = threadIdx.x >> 5, l = lane_id();
@@ -148,7 +152,7 @@ __global__ void __launch_bounds__(192) k_huff_lengths(S4Params p)
    const i32 alpha = (i32)p.ninuse[b] + 2;
    const i32* freq = p.hfreq + ((size_t)b * 6 + t) * BZ_MAX_ALPHA;
    u8* len = p.hlen + ((size_t)b * 6 + t) * BZ_MAX_ALPHA;
-   i32* heap = s_heap[t];
+   u64* hp = s_hp[t];
    i32* wt = s_w[t];
    i32* par = s_par[t];
    for (i32 i = l; i < alpha; i += 32) { const i32 f = freq[i]; wt[i + 1] = (f == 0 ? 1 : f) << 8; }
@@ -156,43 +160,44 @@ __global__ void __launch_bounds__(192) k_huff_lengths(S4Params p)
    for (;;) {
       if (l == 0) {
          i32 nnodes = alpha, nheap = 0;
-         heap[0] = 0; wt[0] = 0; par[0] = -2;
+         hp[0] = 0; par[0] = -2;                        // sentinel: weight 0 at the root's parent slot
          for (i32 i = 1; i <= alpha; i++) {
             par[i] = -1;
             nheap++;
             // sift up
-            i32 z = nheap; const i32 tmp = i; const i32 wtmp = wt[tmp];
-            while (wtmp < wt[heap[z >> 1]]) { heap[z] = heap[z >> 1]; z >>= 1; }
-            heap[z] = tmp;
+            i32 z = nheap; const u32 wtmp = (u32)wt[i];
+            for (;;) { const u64 up = hp[z >> 1]; if (!(wtmp < (u32)(up >> 32))) break; hp[z] = up; z >>= 1; }
+            hp[z] = ((u64)wtmp << 32) | (u32)i;
          }
          while (nheap > 1) {
-            i32 n12[2];
+            u64 n12[2];
 #pragma unroll
             for (int r = 0; r < 2; r++) {
-               n12[r] = heap[1];
-               heap[1] = heap[nheap]; nheap--;
+               n12[r] = hp[1];
+               const u64 tmp = hp[nheap]; nheap--;
                // sift down from the root
-               i32 z = 1; const i32 tmp = heap[1]; const i32 wtmp = wt[tmp];
+               i32 z = 1; const u32 wtmp = (u32)(tmp >> 32);
                for (;;) {
                   i32 y = z << 1;
                   if (y > nheap) break;
-                  if (y < nheap && wt[heap[y + 1]] < wt[heap[y]]) y++;
-                  if (wtmp < wt[heap[y]]) break;
-                  heap[z] = heap[y];
+                  u64 e = hp[y];
+                  if (y < nheap) { const u64 e1 = hp[y + 1]; if ((u32)(e1 >> 32) < (u32)(e >> 32)) { y++; e = e1; } }
+                  if (wtmp < (u32)(e >> 32)) break;
+                  hp[z] = e;
                   z = y;
                }
-               heap[z] = tmp;
+               hp[z] = tmp;
             }
             nnodes++;
-            par[n12[0]] = par[n12[1]] = nnodes;
-            const u32 wa = (u32)wt[n12[0]], wb = (u32)wt[n12[1]];
+            par[(u32)n12[0]] = par[(u32)n12[1]] = nnodes;
+            const u32 wa = (u32)(n12[0] >> 32), wb = (u32)(n12[1] >> 32);
             const u32 da = wa & 0xff, db = wb & 0xff;
-            wt[nnodes] = (i32)(((wa & 0xffffff00u) + (wb & 0xffffff00u)) | (1u + (da > db ? da : db)));
+            const u32 wn = ((wa & 0xffffff00u) + (wb & 0xffffff00u)) | (1u + (da > db ? da : db));
             par[nnodes] = -1;
             nheap++;
-            i32 z = nheap; const i32 tmp = nnodes; const i32 wtmp = wt[tmp];
-            while (wtmp < wt[heap[z >> 1]]) { heap[z] = heap[z >> 1]; z >>= 1; }
-            heap[z] = tmp;
+            i32 z = nheap;
+            for (;;) { const u64 up = hp[z >> 1]; if (!(wn < (u32)(up >> 32))) break; hp[z] = up; z >>= 1; }
+            hp[z] = ((u64)wn << 32) | (u32)nnodes;
          }
       }
       __syncwarp();
