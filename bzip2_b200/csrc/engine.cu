@@ -145,6 +145,10 @@ static int engine_new(EngineFull** out, int device, int level, size_t window_byt
       e->kg_mode = kg ? (u32)atoi(kg) : 1;
       const char* ss = getenv("BZ2_B200_S2_STREAMS");
       e->s2_streams = ss ? (u32)atoi(ss) : 1;
+      const char* ch = getenv("BZ2_B200_CHAIN");
+      e->chain = ch ? (u32)atoi(ch) : 1;
+      const char* cr = getenv("BZ2_B200_CHAIN_MIN_ROUND");
+      e->chain_min_round = cr ? (u32)atoi(cr) : 2;
    }
    if (window_bytes == 0) window_bytes = (size_t)96 << 20;
    // a window must be able to hold the input of one full block of pure runs (255 -> 5 bytes)

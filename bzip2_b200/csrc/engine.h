@@ -117,6 +117,8 @@ struct Engine {
    u32 radix_min;          // CTA sort classes with at least this many threads use radix passes (1024 = none)
    u32 kg_mode;            // k-gram bucket sort: 0 = count / rank / atomic scatter, 1 = count with arrival index / place
    u32 s2_streams;         // run the size classes of a refinement round on side streams (default on)
+   u32 chain;              // follow repeat chains: sort a segment by the rank at the end of its chain (default on)
+   u32 chain_min_round;    // first refinement round that may use chains
    cudaStream_t aux[3];    // side streams of the BWT rounds
    cudaEvent_t ev_fork, ev_join[3];
    u32 *blockmap;          // [enc_cap/4096 + 2] block id of each 4 KiB chunk of enc

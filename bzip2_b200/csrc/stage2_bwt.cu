@@ -61,6 +61,9 @@ struct S2Params {
    const u32* blockmap;
    u32* power_q;
    u8* inuse; u32* ninuse;
+   const u32* jd;           // [E] repeat-chain length of every position (rounds that follow chains), else null
+   const u32* jq;           // [E] length of the repeat at the block's dominant offset from every position, else null
+   const u32* dstar;        // [g] dominant repeat offset of every block of the sub-batch (0 = none)
 };
 
 __device__ __forceinline__ int seg_class(u32 len)
@@ -296,6 +299,7 @@ __device__ __forceinline__ typename KeyOf<TEXT>::type load_key(const S2Params& p
 {
    u32 t = idx + shift; if (t >= n) t -= n;
    if (TEXT) return (typename KeyOf<TEXT>::type)p.K[xb + t];
+   if (p.jd) { t += p.jd[xb + idx]; if (t >= n) t -= n; }      // key at the end of the segment's repeat chain (2e)
    return (typename KeyOf<TEXT>::type)rk_read(p.rank[xb + t], tag);
 }
 
@@ -316,9 +320,40 @@ __global__ void __launch_bounds__(256) k_refine_small(S2Params p, ListsDev Lout,
    const bool active = vseg && sub < len;
    u32 idx = 0;
    KT key = ~(KT)0;
-   if (active) {
-      idx = p.sa[pos + sub];
-      key = load_key<TEXT>(p, xb, n, idx, shift, round + 1);
+   if (active) idx = p.sa[pos + sub];
+   if (TEXT) {
+      if (active) key = load_key<TEXT>(p, xb, n, idx, shift, round + 1);
+   } else {
+      const u32 head_lane = lane_id() & ~(u32)(LANES - 1);
+      const u32 gm = (LANES == 32) ? FULL : (((1u << (LANES & 31)) - 1u) << head_lane);
+      u32 off = shift;
+      // (a) the segment's chain: every member sees the same length
+      if (p.jd && active) off += p.jd[xb + idx];
+      if (p.jq) {
+         // (b) members that form a progression with the block's dominant repeat offset agree as far as the
+         // shortest of their pairwise repeats reaches, and the rank right behind it separates that pair
+         const u32 ds = vseg ? p.dstar[b - p.b0] : 0u;
+         const u32 nx = idx + ds;                         // not cyclic: a strictly increasing chain cannot close on itself
+         bool has = false;
+#pragma unroll
+         for (int k = 0; k < LANES; k++) {
+            const u32 o = __shfl_sync(FULL, idx, head_lane + k);
+            has |= ((u32)k < len && o == nx);
+         }
+         has = has && active && ds != 0 && nx < n;
+         const u32 nhas = __popc(__ballot_sync(FULL, has) & gm);
+         u32 jm = has ? p.jq[xb + idx] : 0xffffffffu;
+#pragma unroll
+         for (int d = LANES >> 1; d > 0; d >>= 1) jm = min(jm, __shfl_xor_sync(FULL, jm, d));
+         if (vseg && nhas + 1 == len && jm != 0xffffffffu) off = max(off, jm);
+      }
+      u32 y = 0;
+      if (active) {
+         y = idx + off;
+         if (y >= n) y -= n;
+         if (y >= n) y -= n;
+         key = (KT)rk_read(p.rank[xb + y], round + 1);
+      }
    }
 #pragma unroll
    for (int k = 2; k <= LANES; k <<= 1) {
@@ -883,9 +918,43 @@ __global__ void __launch_bounds__(AP_THREADS) k_resolve_periodic(S2Params p, ApL
    const u32 span = mx - mn;
    const u32 step = span / (len - 1);
    if (p.debug && t == 0 && len > 8192) printf("[ap] round %u blk %u len %u mn %u mx %u step %u depth %u n %u\n", round, b, len, mn, mx, step, depth, n);
-   if (step == 0 || step * (len - 1) != span || step > depth) return;       // uniform over the CTA
+   if (step == 0 || step * (len - 1) != span) return;                        // uniform over the CTA
+   // step > depth: the members are not yet known to share a whole period -- unless the step is the block's dominant
+   // repeat offset and the repeat lengths jq[] (2e) say that every pair of neighbours but the top one agrees on at
+   // least `step` symbols.  Then member k is u . member k+1 for all k below the top pair, so all neighbours compare
+   // like the top pair does, and that pair is decided by the ranks right behind its repeat.
+   const bool relaxed = step > depth;
+   if (relaxed && !(p.jq && p.dstar[b - p.b0] == step)) return;
    u32 xpos = mx + step; if (xpos >= n) xpos -= n;
    const u32 gs = pos - xb;
+   bool ascending;
+   if (relaxed) {
+      __shared__ u32 s_jtop;
+      for (u32 i = t; i < len; i += AP_THREADS) {
+         const u32 v = p.sa[pos + i];
+         if ((v - mn) % step) { s_bad = 1; continue; }
+         const u32 k = (v - mn) / step;
+         if (k + 1 < len) {
+            const u32 j = p.jq[xb + v];
+            if (k + 2 < len) { if (j < step) s_bad = 1; }
+            else s_jtop = j;
+         }
+      }
+      __syncthreads();
+      if (s_bad) return;
+      const u32 jtop = s_jtop;
+      if (jtop < step) {
+         u32 ya = mx - step + jtop; if (ya >= n) ya -= n;
+         u32 yb = mx + jtop; if (yb >= n) yb -= n;
+         const u32 ra = rk_read(p.rank[xb + ya], tag), rb = rk_read(p.rank[xb + yb], tag);
+         if (ra == rb) return;
+         ascending = ra < rb;
+      } else {
+         const u32 xr = rk_read(p.rank[xb + xpos], tag);
+         if (xr >= gs && xr < gs + len) return;
+         ascending = xr >= gs + len;
+      }
+   } else {
    if (xpos == mn && (u64)step * len == n) {
       // the progression closes on itself: the block is u^len with |u| = step <= depth, these len rotations are
       // equal for good.  Record the multiplicity and retire the segment instead of doubling up to depth n.
@@ -897,11 +966,12 @@ __global__ void __launch_bounds__(AP_THREADS) k_resolve_periodic(S2Params p, ApL
    // the continuation of the last member must lie outside the segment
    const u32 xr = rk_read(p.rank[xb + xpos], tag);
    if (xr >= gs && xr < gs + len) return;
-   const bool ascending = xr >= gs + len;
+   ascending = xr >= gs + len;
    // 2. every member on the progression?  (members are distinct, so len multiples inside [mn, mx] are all of them)
    for (u32 i = t; i < len; i += AP_THREADS) { const u32 v = p.sa[pos + i]; if ((v - mn) % step) s_bad = 1; }
    __syncthreads();
    if (s_bad) return;
+   }
    // 3. final order and final ranks
    for (u32 i = t; i < len; i += AP_THREADS) {
       const u32 v = p.sa[pos + i];
@@ -913,6 +983,246 @@ __global__ void __launch_bounds__(AP_THREADS) k_resolve_periodic(S2Params p, ApL
    __syncthreads();
    for (u32 i = t; i < len; i += AP_THREADS) p.sa[pos + i] = p.idxB[pos + i];
    if (t == 0) items[seg] = entry & ~(u64)0xfffffu;                          // done: nothing left to sort
+}
+
+// ---- 2e. repeat chains ---------------------------------------------------------------------------
+// Long non-tandem repeats (a file that contains another copy of itself 300 kB further on) leave pairs
+// {a, a+p}, {a+1, a+p+1}, ... unresolved over hundreds of thousands of positions, and plain doubling visits
+// every one of them in each of log2(repeat length / depth) rounds.  But such a segment S is decided exactly
+// where the repeat ends: call S *chained* when the successors {x+1 : x in S} all lie in one unresolved
+// segment.  If S, S+1, ..., S+j-1 are chained, the members of S agree on their first j symbols (the members
+// of every segment agree on their first symbol) and the members of S+j agree to the current depth d, so
+// sorting S by the rank at offset j+d is valid -- the same doubling step, from depth j+d instead of d -- and a
+// whole run of chained segments is resolved in the round that resolves its last one.  The chain flag is a
+// property of the segment, so all members of S see the same j.  k_chain_small/k_chain_warp mark the members
+// of chained segments, k_chain_tiles/k_chain_dist turn the marks into j[x] = distance from x to the next
+// unmarked position of the block (cyclic; 0 everywhere if the block has none: an exact power, left to the
+// depth test), and load_key adds j[x] to the round's shift.  Rotations that are equal (exact powers) are
+// never separated, because their successors are never separated.
+template <int LANES>
+__global__ void __launch_bounds__(256) k_chain_small(S2Params p, const u32* items, u32 count, u32 round, u8* cflag)
+{
+   const u32 gid = blockIdx.x * blockDim.x + threadIdx.x;
+   const u32 seg = gid / LANES;
+   const u32 sub = gid % LANES;
+   const bool vseg = seg < count;
+   const u32 entry = vseg ? items[seg] : 0;
+   const u32 pos = entry & 0x7ffffffu;
+   const u32 len = (entry >> 27) + 1;
+   u32 xb = 0, n = 1;
+   if (vseg) { const u32 b = block_of(p, pos); xb = p.X[b]; n = p.X[b + 1] - xb; }
+   const bool active = vseg && sub < len;
+   u32 idx = 0, r = 0;
+   if (active) {
+      idx = p.sa[pos + sub];
+      u32 t = idx + 1; if (t >= n) t = 0;
+      r = rk_read(p.rank[xb + t], round + 1);
+   }
+   const u32 r0 = __shfl_sync(FULL, r, lane_id() & ~(u32)(LANES - 1));
+   const u32 bal = __ballot_sync(FULL, !active || r == r0);
+   const u32 sh = lane_id() & ~(u32)(LANES - 1);
+   const u32 gm = (LANES == 32) ? FULL : (((1u << (LANES & 31)) - 1u) << sh);
+   if (active && (bal & gm) == gm) cflag[xb + idx] = 1;
+}
+
+// one warp per segment of the CTA-sorted classes; gives up at the first successor that falls elsewhere
+__global__ void __launch_bounds__(256) k_chain_warp(S2Params p, const u64* items, u32 count, u32 round, u8* cflag)
+{
+   const u32 seg = blockIdx.x * 8 + (threadIdx.x >> 5);
+   if (seg >= count) return;
+   const u64 entry = items[seg];
+   const u32 pos = (u32)(entry >> 32);
+   const u32 b = (u32)(entry >> 20) & 0xfffu;
+   const u32 len = (u32)entry & 0xfffffu;
+   if (len == 0) return;                                  // retired by k_resolve_periodic
+   const u32 xb = p.X[b], n = p.X[b + 1] - xb;
+   const u32 l = lane_id();
+   u32 t0 = p.sa[pos] + 1; if (t0 >= n) t0 = 0;
+   const u32 r0 = rk_read(p.rank[xb + t0], round + 1);
+   for (u32 i = l; i < ((len + 31) & ~31u); i += 32) {
+      bool ok = true;
+      if (i < len) {
+         u32 t = p.sa[pos + i] + 1; if (t >= n) t = 0;
+         ok = rk_read(p.rank[xb + t], round + 1) == r0;
+      }
+      if (!__all_sync(FULL, ok)) return;
+   }
+   for (u32 i = l; i < len; i += 32) cflag[xb + p.sa[pos + i]] = 1;
+}
+
+// Votes for the block's dominant repeat offset: the distance between two members of every small segment,
+// counted in a 256-bin hash table per block (warp-aggregated).
+__global__ void __launch_bounds__(256) k_chain_vote(S2Params p, const u32* items, u32 count, u32* vote)
+{
+   const u32 seg = blockIdx.x * blockDim.x + threadIdx.x;
+   const bool v = seg < count;
+   u32 slot = 0xffffffffu, dlt = 0;
+   if (v) {
+      const u32 pos = items[seg] & 0x7ffffffu;
+      const u32 b = block_of(p, pos);
+      const u32 x0 = p.sa[pos], x1 = p.sa[pos + 1];
+      dlt = x0 > x1 ? x0 - x1 : x1 - x0;
+      slot = (b - p.b0) * 256u + ((dlt * 2654435761u) >> 24);
+   }
+   const u32 m = __match_any_sync(FULL, slot);
+   if (v && lane_id() == (u32)(__ffs(m) - 1)) {
+      atomicAdd(&vote[2 * (size_t)slot], __popc(m));
+      vote[2 * (size_t)slot + 1] = dlt;
+   }
+}
+
+// the same vote from the warp- and CTA-sorted classes: (max - min) / (len - 1), the step if the members are a progression
+__global__ void __launch_bounds__(AP_THREADS) k_chain_vote_big(S2Params p, ApLists L, u32* vote)
+{
+   __shared__ u32 red_mn[AP_THREADS / 32], red_mx[AP_THREADS / 32];
+   int cls = 0;
+#pragma unroll
+   for (int c = 1; c < N_BIG_CLASSES; c++) if (blockIdx.x >= L.start[c]) cls = c;
+   const u64 entry = L.items[cls][blockIdx.x - L.start[cls]];
+   const u32 pos = (u32)(entry >> 32);
+   const u32 b = (u32)(entry >> 20) & 0xfffu;
+   const u32 len = (u32)entry & 0xfffffu;
+   if (len < 3) return;
+   const u32 t = threadIdx.x;
+   u32 mn = 0xffffffffu, mx = 0;
+   for (u32 i = t; i < len; i += AP_THREADS) { const u32 v = p.sa[pos + i]; mn = min(mn, v); mx = max(mx, v); }
+#pragma unroll
+   for (int d = 16; d > 0; d >>= 1) { mn = min(mn, __shfl_xor_sync(FULL, mn, d)); mx = max(mx, __shfl_xor_sync(FULL, mx, d)); }
+   if (lane_id() == 0) { red_mn[t >> 5] = mn; red_mx[t >> 5] = mx; }
+   __syncthreads();
+   if (t) return;
+#pragma unroll
+   for (int k = 0; k < AP_THREADS / 32; k++) { mn = min(mn, red_mn[k]); mx = max(mx, red_mx[k]); }
+   const u32 span = mx - mn, step = span / (len - 1);
+   if (step == 0 || step * (len - 1) != span) return;
+   const u32 slot = (b - p.b0) * 256u + ((step * 2654435761u) >> 24);
+   atomicAdd(&vote[2 * (size_t)slot], len);
+   vote[2 * (size_t)slot + 1] = step;
+}
+
+constexpr u32 CH_MIN_VOTES = 2048;
+
+// eq[x] = 1 where x and x + d* (cyclic) are in the same segment, d* the block's most voted offset
+__global__ void __launch_bounds__(256) k_chain_eq(S2Params p, const u32* vote, u32* dstar, u8* eq, u32 round)
+{
+   __shared__ u64 red[8];
+   const u32 b = p.b0 + blockIdx.y;
+   const u32 xb = p.X[b], n = p.X[b + 1] - xb;
+   const u32 t0 = blockIdx.x * 4096u;
+   if (t0 >= n) return;
+   const u32* v = vote + (size_t)blockIdx.y * 512;
+   u64 best = ((u64)v[2 * threadIdx.x] << 32) | v[2 * threadIdx.x + 1];
+#pragma unroll
+   for (int d = 16; d > 0; d >>= 1) best = max(best, __shfl_xor_sync(FULL, best, d));
+   if (lane_id() == 0) red[threadIdx.x >> 5] = best;
+   __syncthreads();
+#pragma unroll
+   for (int k = 0; k < 8; k++) best = max(best, red[k]);
+   u32 ds = (u32)best;
+   if ((u32)(best >> 32) < CH_MIN_VOTES || ds >= n) ds = 0;
+   if (blockIdx.x == 0 && threadIdx.x == 0) dstar[blockIdx.y] = ds;
+   if (ds == 0) return;                                    // eq stays all zero
+   const u32 tag = round + 1;
+#pragma unroll 4
+   for (int k = 0; k < 16; k++) {
+      const u32 i = t0 + (u32)k * 256u + threadIdx.x;
+      if (i < n) {
+         u32 y = i + ds; if (y >= n) y -= n;
+         eq[xb + i] = rk_read(p.rank[xb + i], tag) == rk_read(p.rank[xb + y], tag);
+      }
+   }
+}
+
+constexpr int CH_THREADS = 256;
+constexpr int CH_ITEMS = 16;
+constexpr int CH_TILE = CH_THREADS * CH_ITEMS;
+constexpr u32 CH_NONE = 0xffffffffu;
+
+// first unmarked position of every 4096-position tile of a block
+__global__ void __launch_bounds__(CH_THREADS) k_chain_tiles(S2Params p, const u8* cflag, u32* tilefirst, u32 tpb)
+{
+   __shared__ u32 red[CH_THREADS / 32];
+   const u32 b = p.b0 + blockIdx.y;
+   const u32 xb = p.X[b], n = p.X[b + 1] - xb;
+   const u32 t0 = blockIdx.x * CH_TILE;
+   if (t0 >= n) return;
+   u32 first = CH_NONE;
+#pragma unroll 4
+   for (int k = CH_ITEMS - 1; k >= 0; k--) {
+      const u32 i = t0 + (u32)k * CH_THREADS + threadIdx.x;
+      if (i < n && cflag[xb + i] == 0) first = i;
+   }
+#pragma unroll
+   for (int d = 16; d > 0; d >>= 1) first = min(first, __shfl_xor_sync(FULL, first, d));
+   if (lane_id() == 0) red[threadIdx.x >> 5] = first;
+   __syncthreads();
+   if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 1; k < CH_THREADS / 32; k++) first = min(first, red[k]);
+      tilefirst[(size_t)blockIdx.y * tpb + blockIdx.x] = first;
+   }
+}
+
+// j[x] = distance from x to the next unmarked position at or after it, cyclically inside the block
+__global__ void __launch_bounds__(CH_THREADS) k_chain_dist(S2Params p, const u8* cflag, const u32* tilefirst, u32 tpb, u32* jd)
+{
+   __shared__ u8 sf[CH_TILE];
+   __shared__ u32 sj[CH_TILE];
+   __shared__ u32 wmin[CH_THREADS / 32];
+   __shared__ u32 s_carry;
+   const u32 b = p.b0 + blockIdx.y;
+   const u32 xb = p.X[b], n = p.X[b + 1] - xb;
+   const u32 t0 = blockIdx.x * CH_TILE;
+   if (t0 >= n) return;
+   const u32 ntiles = (n + CH_TILE - 1) / CH_TILE;
+   const u32* tf = tilefirst + (size_t)blockIdx.y * tpb;
+   const u32 t = threadIdx.x, w = t >> 5, l = lane_id();
+#pragma unroll 4
+   for (int k = 0; k < CH_ITEMS; k++) {
+      const u32 s = (u32)k * CH_THREADS + t;
+      sf[s] = (t0 + s < n) ? cflag[xb + t0 + s] : (u8)1;      // positions past the end are transparent: n-1 is followed by 0
+   }
+   if (w == 0) {
+      // the next unmarked position after this tile: the tiles behind it, then (+n) the tiles from 0 up to this one
+      u32 carry = CH_NONE;
+      for (u32 base = 1; base <= ntiles; base += 32) {
+         const u32 i = base + l;
+         u32 tt = blockIdx.x + i;
+         const bool wrap = tt >= ntiles;
+         if (wrap) tt -= ntiles;
+         const u32 v = (i <= ntiles) ? tf[tt] : CH_NONE;
+         const u32 found = __ballot_sync(FULL, v != CH_NONE);
+         if (found) { const int src = __ffs(found) - 1; carry = __shfl_sync(FULL, v + (wrap ? n : 0u), src); break; }
+      }
+      if (l == 0) s_carry = carry;
+   }
+   __syncthreads();
+   // thread t owns tile positions t*16 .. t*16+15
+   u32 mine = CH_NONE;
+#pragma unroll
+   for (int r = CH_ITEMS - 1; r >= 0; r--) if (sf[t * CH_ITEMS + r] == 0) mine = t0 + t * CH_ITEMS + (u32)r;
+   u32 inc = mine;                                            // nearest unmarked position in lanes >= l
+#pragma unroll
+   for (int d = 1; d < 32; d <<= 1) { const u32 o = __shfl_down_sync(FULL, inc, d); if (l + d < 32) inc = min(inc, o); }
+   if (l == 0) wmin[w] = inc;
+   __syncthreads();
+   u32 after = s_carry;
+#pragma unroll
+   for (int ww = CH_THREADS / 32 - 1; ww > 0; ww--) if ((u32)ww > w) after = min(after, wmin[ww]);
+   u32 cur = __shfl_down_sync(FULL, inc, 1);
+   cur = (l == 31) ? after : min(cur, after);
+#pragma unroll
+   for (int r = CH_ITEMS - 1; r >= 0; r--) {
+      const u32 s = t * CH_ITEMS + (u32)r;
+      if (sf[s] == 0) cur = t0 + s;
+      sj[s] = (cur == CH_NONE) ? 0u : cur - (t0 + s);
+   }
+   __syncthreads();
+#pragma unroll 4
+   for (int k = 0; k < CH_ITEMS; k++) {
+      const u32 s = (u32)k * CH_THREADS + t;
+      if (t0 + s < n) jd[xb + t0 + s] = sj[s];
+   }
 }
 
 // ---- 3. last column -------------------------------------------------------------------
@@ -1064,6 +1374,7 @@ int stage2_run(Engine* e, u32 nb, u32 E)
    p.debug = trace_on() ? 1 : 0;
    p.blockmap = e->blockmap;
    p.power_q = e->bt.power_q; p.inuse = e->bt.inuse; p.ninuse = e->bt.ninuse;
+   p.jd = nullptr; p.jq = nullptr; p.dstar = nullptr;
 
    const u32 nchunks = (E >> 12) + 1;
    k_blockmap<<<(nchunks + 255) / 256, 256, 0, st>>>(e->bt.X, nb, e->blockmap, nchunks);     BZ_KCHECK(e);
@@ -1098,6 +1409,7 @@ int stage2_run(Engine* e, u32 nb, u32 E)
       dbg_sync(e, "k-gram phase");
 
       int cur = 0;
+      u64 prev_small = 0, prev_big = 0;
       for (u32 round = 0; ; round++) {
          BZ_CUDA(e, cudaMemcpyAsync(e->h_counts, e->lists.counts[cur], sizeof(u32) * (N_CLASSES), cudaMemcpyDeviceToHost, st));
          BZ_CUDA(e, cudaMemcpyAsync(e->h_scalars + 4, e->s1_scalars + 4, sizeof(u32), cudaMemcpyDeviceToHost, st));
@@ -1136,16 +1448,64 @@ int stage2_run(Engine* e, u32 nb, u32 E)
          // The size classes of one round touch disjoint segments, so they run side by side: the few
          // long-running CTAs of the large and CTA-sort classes overlap the sub-warp classes' tails.
          // tandem repeats: the large class from round 0 on (few segments), every CTA/warp-sorted class from round 2 on
-         if (e->periodic) {
-            ApLists AL;
-            u32 tot = 0;
-            for (int c = 0; c < N_BIG_CLASSES; c++) {
-               AL.items[c] = bi[c];
-               AL.start[c] = tot;
-               if (round >= 2 || c == N_BIG_CLASSES - 1) tot += cnt[N_SMALL_CLASSES + c];
+         // Repeat chains (2e) cost a few passes over the window, so they run only while refinement has stalled: a
+         // sizeable part of the window is still unresolved and the last round removed less than 40 % of it.  The segment
+         // chains serve the sub-warp and warp classes; the dominant-offset repeats also serve the tandem rule.
+         static const u32 minlen[N_CLASSES] = {2, 3, 5, 9, 17, 33, 257, 513, 1025, 2049, 4097, 8193};
+         u64 est_small = 0, est_big = 0;
+         for (int c = 0; c < 6; c++) est_small += (u64)cnt[c] * minlen[c];
+         for (int c = 5; c < N_CLASSES; c++) est_big += (u64)cnt[c] * minlen[c];
+         const bool chain_ok = e->chain && !text && round >= 1;
+         const bool force = e->chain >= 2;                                      // BZ2_B200_CHAIN=2: always (tests)
+         const bool go_small = chain_ok && round >= e->chain_min_round && (force || (est_small >= E / 32 && est_small * 10 >= prev_small * 6));
+         const bool go_big = chain_ok && e->periodic && (force || (est_big >= E / 32 && est_big * 10 >= prev_big * 6));
+         prev_small = est_small; prev_big = est_big;
+         ApLists AL;
+         u32 ap_tot = 0;
+         for (int c = 0; c < N_BIG_CLASSES; c++) {
+            AL.items[c] = bi[c];
+            AL.start[c] = ap_tot;
+            if (round >= 2 || go_big || c == N_BIG_CLASSES - 1) ap_tot += cnt[N_SMALL_CLASSES + c];
+         }
+         AL.start[N_BIG_CLASSES] = ap_tot;
+         p.jd = nullptr; p.jq = nullptr; p.dstar = nullptr;
+         {
+            if (go_small || (go_big && ap_tot)) {
+               u8* const cflag = reinterpret_cast<u8*>(e->kscrB);      // the 64-bit key scratch is idle after round 0
+               u8* const eq = cflag + E;
+               u32* const jd = reinterpret_cast<u32*>(e->kscrA);
+               u32* const jq = jd + E;
+               const u32 tpb = (max_n + CH_TILE - 1) / CH_TILE;
+               u32* const tilefirst = e->hist;                          // idle after the k-gram phase
+               u32* const tilefirst2 = tilefirst + (size_t)g * tpb;
+               u32* const vote = tilefirst2 + (size_t)g * tpb;          // [g][256][2]
+               u32* const dstar = vote + (size_t)g * 512;               // [g]
+               const dim3 ctiles(tpb, g);
+               BZ_CUDA(e, cudaMemsetAsync(cflag, 0, 2 * (size_t)E, st));
+               BZ_CUDA(e, cudaMemsetAsync(vote, 0, sizeof(u32) * 513 * (size_t)g, st));
+               if (go_big && ap_tot) { k_chain_vote_big<<<ap_tot, AP_THREADS, 0, st>>>(p, AL, vote); BZ_KCHECK(e); }
+               if (go_small) {
+                  if (cnt[0]) { k_chain_vote<<<(cnt[0] + 255) / 256, 256, 0, st>>>(p, si[0], cnt[0], vote); BZ_KCHECK(e); }
+                  if (cnt[1]) { k_chain_vote<<<(cnt[1] + 255) / 256, 256, 0, st>>>(p, si[1], cnt[1], vote); BZ_KCHECK(e); }
+                  if (cnt[0]) { k_chain_small<2><<<(u32)(((u64)cnt[0] * 2 + 255) / 256), 256, 0, st>>>(p, si[0], cnt[0], round, cflag);   BZ_KCHECK(e); }
+                  if (cnt[1]) { k_chain_small<4><<<(u32)(((u64)cnt[1] * 4 + 255) / 256), 256, 0, st>>>(p, si[1], cnt[1], round, cflag);   BZ_KCHECK(e); }
+                  if (cnt[2]) { k_chain_small<8><<<(u32)(((u64)cnt[2] * 8 + 255) / 256), 256, 0, st>>>(p, si[2], cnt[2], round, cflag);   BZ_KCHECK(e); }
+                  if (cnt[3]) { k_chain_small<16><<<(u32)(((u64)cnt[3] * 16 + 255) / 256), 256, 0, st>>>(p, si[3], cnt[3], round, cflag); BZ_KCHECK(e); }
+                  if (cnt[4]) { k_chain_small<32><<<(u32)(((u64)cnt[4] * 32 + 255) / 256), 256, 0, st>>>(p, si[4], cnt[4], round, cflag); BZ_KCHECK(e); }
+                  if (cnt[5]) { k_chain_warp<<<(cnt[5] + 7) / 8, 256, 0, st>>>(p, bi[0], cnt[5], round, cflag); BZ_KCHECK(e); }
+                  k_chain_tiles<<<ctiles, CH_THREADS, 0, st>>>(p, cflag, tilefirst, tpb);       BZ_KCHECK(e);
+                  k_chain_dist<<<ctiles, CH_THREADS, 0, st>>>(p, cflag, tilefirst, tpb, jd);    BZ_KCHECK(e);
+                  p.jd = jd;
+               }
+               k_chain_eq<<<ctiles, 256, 0, st>>>(p, vote, dstar, eq, round);                BZ_KCHECK(e);
+               k_chain_tiles<<<ctiles, CH_THREADS, 0, st>>>(p, eq, tilefirst2, tpb);         BZ_KCHECK(e);
+               k_chain_dist<<<ctiles, CH_THREADS, 0, st>>>(p, eq, tilefirst2, tpb, jq);      BZ_KCHECK(e);
+               p.jq = jq; p.dstar = dstar;
+               dbg_sync(e, "repeat chains");
             }
-            AL.start[N_BIG_CLASSES] = tot;
-            if (tot) { k_resolve_periodic<<<tot, AP_THREADS, 0, st>>>(p, AL, round); BZ_KCHECK(e); }
+         }
+         if (e->periodic && ap_tot) {
+            k_resolve_periodic<<<ap_tot, AP_THREADS, 0, st>>>(p, AL, round); BZ_KCHECK(e);
             dbg_sync(e, "k_resolve_periodic");
          }
          const bool fork = e->s2_streams && total > 64;
