@@ -713,15 +713,16 @@ __global__ void __launch_bounds__(THREADS) k_refine_radix(S2Params p, ListsDev L
 }
 
 // ---- 2c. large segments: one CTA, stable LSD radix passes ----------------------------
-constexpr int LG_THREADS = 1024;
 constexpr int LG_ITEMS = 4;
-constexpr int LG_TILE = LG_THREADS * LG_ITEMS;
-constexpr int LG_WARPS = LG_THREADS / 32;
 constexpr int LG_MAXPASS = 7;
 
-template <bool TEXT>
-__global__ void __launch_bounds__(LG_THREADS) k_refine_large(S2Params p, ListsDev Lout, const u64* items, u32 round)
+// LG_THREADS = 1024: one CTA per SM (64 registers per thread).  512 with two CTAs per SM (one sorts while the other
+// waits at a barrier) was measured: no gain (text 50.1 vs 50.9 ms of S2 per 400 MB).
+template <bool TEXT, int LG_THREADS>
+__global__ void __launch_bounds__(LG_THREADS, 1024 / LG_THREADS) k_refine_large(S2Params p, ListsDev Lout, const u64* items, u32 round)
 {
+   constexpr int LG_TILE = LG_THREADS * LG_ITEMS;
+   constexpr int LG_WARPS = LG_THREADS / 32;
    typedef typename KeyOf<TEXT>::type KT;
    __shared__ u32 whist[LG_WARPS][256];
    __shared__ u32 binbase[TEXT ? LG_MAXPASS : 3][256];
@@ -994,13 +995,13 @@ __global__ void __launch_bounds__(AP_THREADS) k_resolve_periodic(S2Params p, ApL
 // of every segment agree on their first symbol) and the members of S+j agree to the current depth d, so
 // sorting S by the rank at offset j+d is valid -- the same doubling step, from depth j+d instead of d -- and a
 // whole run of chained segments is resolved in the round that resolves its last one.  The chain flag is a
-// property of the segment, so all members of S see the same j.  k_chain_small/k_chain_warp mark the members
-// of chained segments, k_chain_tiles/k_chain_dist turn the marks into j[x] = distance from x to the next
+// property of the segment, so all members of S see the same j.  k_rep_small/k_rep_warp mark the members
+// of chained segments, k_rep_tiles/k_rep_dist turn the marks into j[x] = distance from x to the next
 // unmarked position of the block (cyclic; 0 everywhere if the block has none: an exact power, left to the
 // depth test), and load_key adds j[x] to the round's shift.  Rotations that are equal (exact powers) are
 // never separated, because their successors are never separated.
 template <int LANES>
-__global__ void __launch_bounds__(256) k_chain_small(S2Params p, const u32* items, u32 count, u32 round, u8* cflag)
+__global__ void __launch_bounds__(256) k_rep_small(S2Params p, const u32* items, u32 count, u32 round, u8* cflag)
 {
    const u32 gid = blockIdx.x * blockDim.x + threadIdx.x;
    const u32 seg = gid / LANES;
@@ -1026,7 +1027,7 @@ __global__ void __launch_bounds__(256) k_chain_small(S2Params p, const u32* item
 }
 
 // one warp per segment of the CTA-sorted classes; gives up at the first successor that falls elsewhere
-__global__ void __launch_bounds__(256) k_chain_warp(S2Params p, const u64* items, u32 count, u32 round, u8* cflag)
+__global__ void __launch_bounds__(256) k_rep_warp(S2Params p, const u64* items, u32 count, u32 round, u8* cflag)
 {
    const u32 seg = blockIdx.x * 8 + (threadIdx.x >> 5);
    if (seg >= count) return;
@@ -1052,9 +1053,10 @@ __global__ void __launch_bounds__(256) k_chain_warp(S2Params p, const u64* items
 
 // Votes for the block's dominant repeat offset: the distance between two members of every small segment,
 // counted in a 256-bin hash table per block (warp-aggregated).
-__global__ void __launch_bounds__(256) k_chain_vote(S2Params p, const u32* items, u32 count, u32* vote)
+constexpr u32 REP_VOTE_STRIDE = 4;
+__global__ void __launch_bounds__(256) k_rep_vote(S2Params p, const u32* items, u32 count, u32* vote)
 {
-   const u32 seg = blockIdx.x * blockDim.x + threadIdx.x;
+   const u32 seg = (blockIdx.x * blockDim.x + threadIdx.x) * REP_VOTE_STRIDE;     // a sample is enough
    const bool v = seg < count;
    u32 slot = 0xffffffffu, dlt = 0;
    if (v) {
@@ -1072,7 +1074,7 @@ __global__ void __launch_bounds__(256) k_chain_vote(S2Params p, const u32* items
 }
 
 // the same vote from the warp- and CTA-sorted classes: (max - min) / (len - 1), the step if the members are a progression
-__global__ void __launch_bounds__(AP_THREADS) k_chain_vote_big(S2Params p, ApLists L, u32* vote)
+__global__ void __launch_bounds__(AP_THREADS) k_rep_vote_big(S2Params p, ApLists L, u32* vote)
 {
    __shared__ u32 red_mn[AP_THREADS / 32], red_mx[AP_THREADS / 32];
    int cls = 0;
@@ -1100,10 +1102,10 @@ __global__ void __launch_bounds__(AP_THREADS) k_chain_vote_big(S2Params p, ApLis
    vote[2 * (size_t)slot + 1] = step;
 }
 
-constexpr u32 CH_MIN_VOTES = 2048;
+constexpr u32 CH_MIN_VOTES = 512;       // sampled small segments count 1, progressions their length
 
 // eq[x] = 1 where x and x + d* (cyclic) are in the same segment, d* the block's most voted offset
-__global__ void __launch_bounds__(256) k_chain_eq(S2Params p, const u32* vote, u32* dstar, u8* eq, u32 round)
+__global__ void __launch_bounds__(256) k_rep_eq(S2Params p, const u32* vote, u32* dstar, u8* eq, u32 round)
 {
    __shared__ u64 red[8];
    const u32 b = p.b0 + blockIdx.y;
@@ -1139,7 +1141,7 @@ constexpr int CH_TILE = CH_THREADS * CH_ITEMS;
 constexpr u32 CH_NONE = 0xffffffffu;
 
 // first unmarked position of every 4096-position tile of a block
-__global__ void __launch_bounds__(CH_THREADS) k_chain_tiles(S2Params p, const u8* cflag, u32* tilefirst, u32 tpb)
+__global__ void __launch_bounds__(CH_THREADS) k_rep_tiles(S2Params p, const u8* cflag, u32* tilefirst, u32 tpb)
 {
    __shared__ u32 red[CH_THREADS / 32];
    const u32 b = p.b0 + blockIdx.y;
@@ -1164,10 +1166,10 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain_tiles(S2Params p, const u8
 }
 
 // j[x] = distance from x to the next unmarked position at or after it, cyclically inside the block
-__global__ void __launch_bounds__(CH_THREADS) k_chain_dist(S2Params p, const u8* cflag, const u32* tilefirst, u32 tpb, u32* jd)
+__global__ void __launch_bounds__(CH_THREADS) k_rep_dist(S2Params p, const u8* cflag, const u32* tilefirst, u32 tpb, u32* jd)
 {
-   __shared__ u8 sf[CH_TILE];
-   __shared__ u32 sj[CH_TILE];
+   __shared__ __align__(16) u8 sf[CH_TILE];
+   __shared__ u32 sj[CH_TILE + CH_TILE / 32];                 // index s + s/32: conflict-free for both the blocked and the striped view
    __shared__ u32 wmin[CH_THREADS / 32];
    __shared__ u32 s_carry;
    const u32 b = p.b0 + blockIdx.y;
@@ -1198,9 +1200,11 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain_dist(S2Params p, const u8*
    }
    __syncthreads();
    // thread t owns tile positions t*16 .. t*16+15
+   const uint4 f4 = *reinterpret_cast<const uint4*>(&sf[t * CH_ITEMS]);
+   const u32 fw[4] = {f4.x, f4.y, f4.z, f4.w};
    u32 mine = CH_NONE;
 #pragma unroll
-   for (int r = CH_ITEMS - 1; r >= 0; r--) if (sf[t * CH_ITEMS + r] == 0) mine = t0 + t * CH_ITEMS + (u32)r;
+   for (int r = CH_ITEMS - 1; r >= 0; r--) if (((fw[r >> 2] >> (8 * (r & 3))) & 255u) == 0) mine = t0 + t * CH_ITEMS + (u32)r;
    u32 inc = mine;                                            // nearest unmarked position in lanes >= l
 #pragma unroll
    for (int d = 1; d < 32; d <<= 1) { const u32 o = __shfl_down_sync(FULL, inc, d); if (l + d < 32) inc = min(inc, o); }
@@ -1214,14 +1218,14 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain_dist(S2Params p, const u8*
 #pragma unroll
    for (int r = CH_ITEMS - 1; r >= 0; r--) {
       const u32 s = t * CH_ITEMS + (u32)r;
-      if (sf[s] == 0) cur = t0 + s;
-      sj[s] = (cur == CH_NONE) ? 0u : cur - (t0 + s);
+      if (((fw[r >> 2] >> (8 * (r & 3))) & 255u) == 0) cur = t0 + s;
+      sj[s + (s >> 5)] = (cur == CH_NONE) ? 0u : cur - (t0 + s);
    }
    __syncthreads();
 #pragma unroll 4
    for (int k = 0; k < CH_ITEMS; k++) {
       const u32 s = (u32)k * CH_THREADS + t;
-      if (t0 + s < n) jd[xb + t0 + s] = sj[s];
+      if (t0 + s < n) jd[xb + t0 + s] = sj[s + (s >> 5)];
    }
 }
 
@@ -1351,6 +1355,13 @@ static void launch_radix(Engine* e, cudaStream_t st, const S2Params& p, const Li
    if (text) k_refine_radix<THREADS, true><<<count, THREADS, CAP * sizeof(u64), st>>>(p, Lout, items, count, round);
    else      k_refine_radix<THREADS, false><<<count, THREADS, CAP * (CAP > 4096 ? sizeof(u64) : sizeof(u32)), st>>>(p, Lout, items, count, round);
    char nm[64]; snprintf(nm, sizeof nm, "k_refine_radix<%d,%d> count=%u round=%u", THREADS, (int)text, count, round); dbg_sync(e, nm);
+}
+
+static void launch_large(Engine* e, cudaStream_t st, const S2Params& p, const ListsDev& Lout, const u64* items, u32 count, u32 round, bool text)
+{
+   if (text) k_refine_large<true, 1024><<<count, 1024, 0, st>>>(p, Lout, items, round);
+   else      k_refine_large<false, 1024><<<count, 1024, 0, st>>>(p, Lout, items, round);
+   dbg_sync(e, "k_refine_large");
 }
 
 // the 8192-element radix sort keeps 64 KiB of sort words in dynamic shared memory
@@ -1483,23 +1494,23 @@ int stage2_run(Engine* e, u32 nb, u32 E)
                const dim3 ctiles(tpb, g);
                BZ_CUDA(e, cudaMemsetAsync(cflag, 0, 2 * (size_t)E, st));
                BZ_CUDA(e, cudaMemsetAsync(vote, 0, sizeof(u32) * 513 * (size_t)g, st));
-               if (go_big && ap_tot) { k_chain_vote_big<<<ap_tot, AP_THREADS, 0, st>>>(p, AL, vote); BZ_KCHECK(e); }
+               if (go_big && ap_tot) { k_rep_vote_big<<<ap_tot, AP_THREADS, 0, st>>>(p, AL, vote); BZ_KCHECK(e); }
                if (go_small) {
-                  if (cnt[0]) { k_chain_vote<<<(cnt[0] + 255) / 256, 256, 0, st>>>(p, si[0], cnt[0], vote); BZ_KCHECK(e); }
-                  if (cnt[1]) { k_chain_vote<<<(cnt[1] + 255) / 256, 256, 0, st>>>(p, si[1], cnt[1], vote); BZ_KCHECK(e); }
-                  if (cnt[0]) { k_chain_small<2><<<(u32)(((u64)cnt[0] * 2 + 255) / 256), 256, 0, st>>>(p, si[0], cnt[0], round, cflag);   BZ_KCHECK(e); }
-                  if (cnt[1]) { k_chain_small<4><<<(u32)(((u64)cnt[1] * 4 + 255) / 256), 256, 0, st>>>(p, si[1], cnt[1], round, cflag);   BZ_KCHECK(e); }
-                  if (cnt[2]) { k_chain_small<8><<<(u32)(((u64)cnt[2] * 8 + 255) / 256), 256, 0, st>>>(p, si[2], cnt[2], round, cflag);   BZ_KCHECK(e); }
-                  if (cnt[3]) { k_chain_small<16><<<(u32)(((u64)cnt[3] * 16 + 255) / 256), 256, 0, st>>>(p, si[3], cnt[3], round, cflag); BZ_KCHECK(e); }
-                  if (cnt[4]) { k_chain_small<32><<<(u32)(((u64)cnt[4] * 32 + 255) / 256), 256, 0, st>>>(p, si[4], cnt[4], round, cflag); BZ_KCHECK(e); }
-                  if (cnt[5]) { k_chain_warp<<<(cnt[5] + 7) / 8, 256, 0, st>>>(p, bi[0], cnt[5], round, cflag); BZ_KCHECK(e); }
-                  k_chain_tiles<<<ctiles, CH_THREADS, 0, st>>>(p, cflag, tilefirst, tpb);       BZ_KCHECK(e);
-                  k_chain_dist<<<ctiles, CH_THREADS, 0, st>>>(p, cflag, tilefirst, tpb, jd);    BZ_KCHECK(e);
+                  if (cnt[0]) { k_rep_vote<<<(cnt[0] / REP_VOTE_STRIDE + 256) / 256, 256, 0, st>>>(p, si[0], cnt[0], vote); BZ_KCHECK(e); }
+                  if (cnt[1]) { k_rep_vote<<<(cnt[1] / REP_VOTE_STRIDE + 256) / 256, 256, 0, st>>>(p, si[1], cnt[1], vote); BZ_KCHECK(e); }
+                  if (cnt[0]) { k_rep_small<2><<<(u32)(((u64)cnt[0] * 2 + 255) / 256), 256, 0, st>>>(p, si[0], cnt[0], round, cflag);   BZ_KCHECK(e); }
+                  if (cnt[1]) { k_rep_small<4><<<(u32)(((u64)cnt[1] * 4 + 255) / 256), 256, 0, st>>>(p, si[1], cnt[1], round, cflag);   BZ_KCHECK(e); }
+                  if (cnt[2]) { k_rep_small<8><<<(u32)(((u64)cnt[2] * 8 + 255) / 256), 256, 0, st>>>(p, si[2], cnt[2], round, cflag);   BZ_KCHECK(e); }
+                  if (cnt[3]) { k_rep_small<16><<<(u32)(((u64)cnt[3] * 16 + 255) / 256), 256, 0, st>>>(p, si[3], cnt[3], round, cflag); BZ_KCHECK(e); }
+                  if (cnt[4]) { k_rep_small<32><<<(u32)(((u64)cnt[4] * 32 + 255) / 256), 256, 0, st>>>(p, si[4], cnt[4], round, cflag); BZ_KCHECK(e); }
+                  if (cnt[5]) { k_rep_warp<<<(cnt[5] + 7) / 8, 256, 0, st>>>(p, bi[0], cnt[5], round, cflag); BZ_KCHECK(e); }
+                  k_rep_tiles<<<ctiles, CH_THREADS, 0, st>>>(p, cflag, tilefirst, tpb);       BZ_KCHECK(e);
+                  k_rep_dist<<<ctiles, CH_THREADS, 0, st>>>(p, cflag, tilefirst, tpb, jd);    BZ_KCHECK(e);
                   p.jd = jd;
                }
-               k_chain_eq<<<ctiles, 256, 0, st>>>(p, vote, dstar, eq, round);                BZ_KCHECK(e);
-               k_chain_tiles<<<ctiles, CH_THREADS, 0, st>>>(p, eq, tilefirst2, tpb);         BZ_KCHECK(e);
-               k_chain_dist<<<ctiles, CH_THREADS, 0, st>>>(p, eq, tilefirst2, tpb, jq);      BZ_KCHECK(e);
+               k_rep_eq<<<ctiles, 256, 0, st>>>(p, vote, dstar, eq, round);                BZ_KCHECK(e);
+               k_rep_tiles<<<ctiles, CH_THREADS, 0, st>>>(p, eq, tilefirst2, tpb);         BZ_KCHECK(e);
+               k_rep_dist<<<ctiles, CH_THREADS, 0, st>>>(p, eq, tilefirst2, tpb, jq);      BZ_KCHECK(e);
                p.jq = jq; p.dstar = dstar;
                dbg_sync(e, "repeat chains");
             }
@@ -1516,14 +1527,12 @@ int stage2_run(Engine* e, u32 nb, u32 E)
             for (int a = 0; a < 3; a++) BZ_CUDA(e, cudaStreamWaitEvent(e->aux[a], e->ev_fork, 0));
          }
          if (cnt[CLS_LARGE]) {
-            if (text) k_refine_large<true><<<cnt[CLS_LARGE], LG_THREADS, 0, sL>>>(p, Lout, bi[6], round);
-            else      k_refine_large<false><<<cnt[CLS_LARGE], LG_THREADS, 0, sL>>>(p, Lout, bi[6], round);
+            launch_large(e, sL, p, Lout, bi[6], cnt[CLS_LARGE], round, text);
             dbg_sync(e, "k_refine_large");
          }
          if (cnt[CLS_C8K]) {
             if (e->radix_c8k) launch_radix<1024>(e, sL, p, Lout, bi[5], cnt[CLS_C8K], round, text);
-            else if (text) k_refine_large<true><<<cnt[CLS_C8K], LG_THREADS, 0, sL>>>(p, Lout, bi[5], round);
-            else           k_refine_large<false><<<cnt[CLS_C8K], LG_THREADS, 0, sL>>>(p, Lout, bi[5], round);
+            else launch_large(e, sL, p, Lout, bi[5], cnt[CLS_C8K], round, text);
          }
          const u32 rx = e->radix_min;            // smallest CTA class sorted by radix passes instead of the bitonic network
          if (cnt[CLS_C4K])   { if (rx <= 512) launch_radix<512>(e, sM, p, Lout, bi[4], cnt[CLS_C4K], round, text); else launch_medium<512>(e, sM, p, Lout, bi[4], cnt[CLS_C4K], round, text); }

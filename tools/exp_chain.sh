@@ -1,10 +1,9 @@
 #!/bin/bash
-# repeat-chain experiment: full GPU suite, then the workloads with default settings
 set -u
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 O=gpurun_out
 rm -f $O/chain.log
-timeout 900 python -m pytest tests -x -q -m gpu > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/chain.log
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "long_repeats or chains_from or periodic_segments or stage_outputs or exact_power or fuzz_small or golden_streams" > $O/pytest_chain.log 2>&1; echo "pytest rc=$?" >> $O/chain.log
 run() {
   echo "== $*" >> $O/chain.log
   env "$@" timeout 300 python bench.py --mb 400 --steps 3 --warmup 2 --no-e2e --no-cpu --workload $WL 2>&1 | python -c "
@@ -15,6 +14,8 @@ for l in sys.stdin:
     print(j['value'], j['ms_per_step'], j['roofline']['stage_ms'], 'rounds', j['bwt_rounds'])
 " >> $O/chain.log 2>&1
 }
-for WL in mixed text period1000 aab random runs; do
-  run WL=$WL BZ2_B200_CHAIN=1
+for WL in text mixed; do
+  run WL=$WL BZ2_B200_LG_THREADS=1024
+  run WL=$WL BZ2_B200_LG_THREADS=512
 done
+WL=period1000; run WL=$WL BZ2_B200_LG_THREADS=1024

@@ -8,8 +8,8 @@ import csv
 import json
 import re
 
-STAGE = [("S1", r"k_tile|k_scan_runs|k_scan_u32|k_chain|k_crc|k_blockmap"),
-         ("S2", r"k_inuse|k_codemap|k_kgram|k_seg_init|k_refine|k_bwt_out"),
+STAGE = [("S1", r"k_tile|k_scan_runs|k_scan_u32|k_chain$|k_chain_from|k_crc|k_blockmap"),
+         ("S2", r"k_inuse|k_codemap|k_kgram|k_seg_init|k_refine|k_resolve|k_rep_|k_power|k_bwt_out"),
          ("S3", r"k_mtf|k_rle2"),
          ("S4", r"k_huff|k_bit_offsets|k_group_scan|k_pack|k_pre_copy|k_put_bits|k_concat")]
 
