@@ -304,6 +304,48 @@ __device__ __forceinline__ typename KeyOf<TEXT>::type load_key(const S2Params& p
 }
 
 // ---- 2a. small segments: sub-warp bitonic network, one element per lane --------------------
+template <int LANES, typename KT>
+__device__ __forceinline__ void small_sort(KT& key, u32& idx, const u32 sub)
+{
+#pragma unroll
+   for (int k = 2; k <= LANES; k <<= 1) {
+#pragma unroll
+      for (int j = k >> 1; j > 0; j >>= 1) {
+         const KT ok = __shfl_xor_sync(FULL, key, j);
+         const u32 oi = __shfl_xor_sync(FULL, idx, j);
+         const bool asc = ((sub & k) == 0);
+         const bool low = ((sub & j) == 0);
+         const bool take = (asc == low) ? (ok < key) : (ok > key);
+         if (take) { key = ok; idx = oi; }
+      }
+   }
+}
+
+// group boundaries of the sorted lanes, new ranks, next-round segments
+template <int LANES, typename KT>
+__device__ __forceinline__ void small_finish(const S2Params& p, const ListsDev& Lout, const KT key, const u32 idx, const u32 sub, const bool active,
+                                             const u32 len, const u32 pos, const u32 xb, const u32 b, const u32 n, const u32 depth, const u32 round)
+{
+   const KT pk = __shfl_up_sync(FULL, key, 1);
+   const KT nk = __shfl_down_sync(FULL, key, 1);
+   const bool head = active && (sub == 0 || pk != key);
+   const u32 bal = __ballot_sync(FULL, head);
+   const u32 sh = lane_id() & ~(u32)(LANES - 1);
+   const u32 mask = (LANES == 32) ? bal : ((bal >> sh) & ((1u << (LANES & 31)) - 1u));
+   const u32 below = mask & ((2u << sub) - 1u);
+   const u32 gstart = active ? (31 - __clz(below)) : 0;
+   const bool is_end = active && (sub == len - 1 || nk != key);
+   const u32 size = sub - gstart + 1;
+   if (active) {
+      p.sa[pos + sub] = idx;
+      p.rank[xb + idx] = rk_pack(round + 1, pos - xb, (pos - xb) + gstart);
+   }
+   const bool multi = is_end && size >= 2;
+   const bool deep = (depth >= n);
+   if (multi && deep) atomicMax(&p.power_q[b], size);
+   push_seg(Lout, multi && !deep, pos + gstart, b, size);
+}
+
 template <int LANES, bool TEXT>
 __global__ void __launch_bounds__(256) k_refine_small(S2Params p, ListsDev Lout, const u32* items, u32 count, u32 round)
 {
@@ -318,7 +360,7 @@ __global__ void __launch_bounds__(256) k_refine_small(S2Params p, ListsDev Lout,
    u32 b = 0, xb = 0, n = 1, shift = 0, depth = 0;
    if (vseg) { b = block_of(p, pos); xb = p.X[b]; n = p.X[b + 1] - xb; shift = round_shift(p, b, round, &depth); }
    const bool active = vseg && sub < len;
-   u32 idx = 0;
+   u32 idx = 0, off0 = 0;
    KT key = ~(KT)0;
    if (active) idx = p.sa[pos + sub];
    if (TEXT) {
@@ -354,37 +396,56 @@ __global__ void __launch_bounds__(256) k_refine_small(S2Params p, ListsDev Lout,
          if (y >= n) y -= n;
          key = (KT)rk_read(p.rank[xb + y], round + 1);
       }
+      off0 = off;
    }
+   small_sort<LANES, KT>(key, idx, sub);
+   if (!TEXT && LANES >= 4 && LANES <= 8 && p.jq) {
+      // More keys in the same visit: a group of equal keys that is again a progression with the dominant offset is
+      // decided where the shortest of ITS pairwise repeats ends (a triple a, a+p, a+2p loses a+2p to the first key and
+      // is finished by the second).  The group index stands for everything compared so far.
+      const u32 head_lane = lane_id() & ~(u32)(LANES - 1);
+      const u32 ds = vseg ? p.dstar[b - p.b0] : 0u;
+      u64 ck = active ? (u64)key : ~(u64)0;
+      u32 offc = off0;                                   // what the lane's group agrees on; the group keeps its lanes through every sort
+      for (int it = 0; it < LANES - 2; it++) {
+         const u64 pk = __shfl_up_sync(FULL, ck, 1);
+         const bool head = active && (sub == 0 || pk != ck);
+         const u32 bal = __ballot_sync(FULL, head);
+         const u32 mask = (bal >> head_lane) & ((1u << LANES) - 1u);
+         const u32 gstart = active ? (31 - __clz(mask & ((2u << sub) - 1u))) : 0xffu;
+         const u32 nx = idx + ds;
+         bool has = false;
 #pragma unroll
-   for (int k = 2; k <= LANES; k <<= 1) {
+         for (int k = 0; k < LANES; k++) {
+            const u32 oi = __shfl_sync(FULL, idx, head_lane + k);
+            const u32 og = __shfl_sync(FULL, gstart, head_lane + k);
+            has |= (og == gstart && oi == nx);
+         }
+         has = has && active && ds != 0 && nx < n;
+         const u32 jv = has ? p.jq[xb + idx] : 0xffffffffu;
+         u32 size = 0, nh = 0, jm = 0xffffffffu;
 #pragma unroll
-      for (int j = k >> 1; j > 0; j >>= 1) {
-         const KT ok = __shfl_xor_sync(FULL, key, j);
-         const u32 oi = __shfl_xor_sync(FULL, idx, j);
-         const bool asc = ((sub & k) == 0);
-         const bool low = ((sub & j) == 0);
-         const bool take = (asc == low) ? (ok < key) : (ok > key);
-         if (take) { key = ok; idx = oi; }
+         for (int k = 0; k < LANES; k++) {
+            const u32 og = __shfl_sync(FULL, gstart, head_lane + k);
+            const u32 oh = __shfl_sync(FULL, (u32)has, head_lane + k);
+            const u32 oj = __shfl_sync(FULL, jv, head_lane + k);
+            if (og == gstart) { size++; nh += oh; jm = min(jm, oj); }
+         }
+         const bool refine = active && size >= 2 && nh + 1 == size && jm != 0xffffffffu && jm > offc;
+         if (!__any_sync(FULL, refine)) break;
+         u32 k2 = 0;
+         if (refine) {
+            u32 y = idx + jm; if (y >= n) y -= n;
+            k2 = rk_read(p.rank[xb + y], round + 1);
+            offc = jm;
+         }
+         ck = active ? (((u64)gstart << 32) | k2) : ~(u64)0;
+         small_sort<LANES, u64>(ck, idx, sub);
       }
+      small_finish<LANES, u64>(p, Lout, ck, idx, sub, active, len, pos, xb, b, n, depth, round);
+   } else {
+      small_finish<LANES, KT>(p, Lout, key, idx, sub, active, len, pos, xb, b, n, depth, round);
    }
-   const KT pk = __shfl_up_sync(FULL, key, 1);
-   const KT nk = __shfl_down_sync(FULL, key, 1);
-   const bool head = active && (sub == 0 || pk != key);
-   const u32 bal = __ballot_sync(FULL, head);
-   const u32 sh = lane_id() & ~(u32)(LANES - 1);
-   const u32 mask = (LANES == 32) ? bal : ((bal >> sh) & ((1u << (LANES & 31)) - 1u));
-   const u32 below = mask & ((2u << sub) - 1u);
-   const u32 gstart = active ? (31 - __clz(below)) : 0;
-   const bool is_end = active && (sub == len - 1 || nk != key);
-   const u32 size = sub - gstart + 1;
-   if (active) {
-      p.sa[pos + sub] = idx;
-      p.rank[xb + idx] = rk_pack(round + 1, pos - xb, (pos - xb) + gstart);
-   }
-   const bool multi = is_end && size >= 2;
-   const bool deep = (depth >= n);
-   if (multi && deep) atomicMax(&p.power_q[b], size);
-   push_seg(Lout, multi && !deep, pos + gstart, b, size);
 }
 
 // ---- 2b. medium segments: bitonic sort of packed (key, local index) words ----------------

@@ -203,6 +203,7 @@ def _long_repeat_cases():
     few = rng.integers(0, 4, 5_000, dtype=np.uint8) + 65
     return [
         ("random300k_x3", np.resize(r300, 2_000_000)),                      # every rotation has a twin 300 kB further on
+        ("random130k_x7", np.resize(r300[:130_000], 1_700_000)),            # up to seven copies per block: several keys per visit
         ("text_twice_edited", np.concatenate([txt, edited, txt[:150_000]])),
         ("binary_tiled", np.resize(binary, 1_900_000)),                     # the C4 binary third
         ("period5000_4sym", np.resize(few, 1_500_000)),

@@ -14,8 +14,6 @@ for l in sys.stdin:
     print(j['value'], j['ms_per_step'], j['roofline']['stage_ms'], 'rounds', j['bwt_rounds'])
 " >> $O/chain.log 2>&1
 }
-for WL in text mixed; do
-  run WL=$WL BZ2_B200_LG_THREADS=1024
-  run WL=$WL BZ2_B200_LG_THREADS=512
+for WL in text mixed period1000; do
+  run WL=$WL BZ2_B200_CHAIN=1
 done
-WL=period1000; run WL=$WL BZ2_B200_LG_THREADS=1024
