@@ -434,9 +434,9 @@ def main():
     except Exception:  # noqa: BLE001
         pass
     roof = {"bound": "hbm",
-            "kernel": "S2 BWT kernel family (k_kgram*, k_refine_*, k_bwt_out; ~70 launches per 100 MB window), timed live by CUDA events "
+            "kernel": "S2 BWT kernel family (k_kgram*, k_refine_*, k_resolve_periodic, k_rep_*, k_bwt_out; ~70 launches per 100 MB window), timed live by CUDA events "
                       "around the stage on the launching stream; top single kernel k_refine_large<true> = 10% of the step "
-                      "(profiles/r01_v4_launch_summary_text100MB.md)",
+                      "(profiles/r01_v6_launch_summary.md)",
             "algorithmic_bytes": int(s2_bytes), "algorithmic_rule": "2*rho bytes per input byte: read the block once, write the last column once (SURVEY 8d)",
             "achieved": round(s2_bytes / (stage_ms[2] * 1e-3) / 1e9, 3), "peak": peak, "unit": "GB/s",
             "frac": round(s2_bytes / (stage_ms[2] * 1e-3) / 1e9 / peak, 6), "traffic": traffic, "peak_source": peak_src,

@@ -6,21 +6,22 @@
 // order; output byte k is the byte preceding rotation k; origPtr is the rank of
 // rotation 0.  The method is not the reference's (induced sorting is serial):
 //
-//   1. bigram bucket sort   every rotation is counted into one of 65536 buckets by
-//                           its first two bytes (global atomics), buckets are
-//                           scanned, rotations scattered -> h-order with h = 2.
-//   2. prefix doubling      each unresolved bucket ("segment") is sorted by the rank
-//                           of the rotation h further on (cyclic), which doubles the
-//                           sorted depth; equal keys stay one segment.  Segments are
-//                           handled by size class, all blocks of the window at once:
-//                             2..32       sub-warp bitonic network in registers
-//                             33..4096    one CTA, bitonic sort in shared memory
-//                             > 4096      one CTA, stable 8-bit LSD radix passes
-//                                         staged through shared-memory histograms
-//                           New ranks are written by sorted position and applied in
-//                           a second kernel so that a round only ever reads h-order
-//                           ranks.
-//   3. last column          bwt[k] = T[(sa[k]-1) mod n]; origPtr = k with sa[k]==0.
+//   1. k-gram bucket sort   the first k symbols of every rotation, packed in base-`ninuse` notation, select one
+//                           of up to 2^18 buckets per block (text: k = 3, bytes: k = 2, a binary alphabet: k = 18);
+//                           one atomic pass keeps each rotation's arrival index, a scan and a placement pass
+//                           follow.  The placement pass also writes K[i], the next m symbols of i in <= 51 bits.
+//   2. round 0              every bucket ("segment") is sorted by the text key K[i+k]: depth k -> k+m.
+//   3. prefix doubling      every unresolved segment is sorted by the rank of the rotation d further on (cyclic),
+//                           d = current depth; equal keys stay one segment.  Ranks are tagged two-generation words
+//                           updated in place (rk_pack).  Segments are handled by size class, all blocks of the
+//                           window in the same launch, the classes of a round on side streams:
+//                             2..32       sub-warp bitonic network in registers        (k_refine_small)
+//                             33..512     warp / 64-thread CTA, packed-word bitonic    (k_refine_medium)
+//                             513..8192   CTA-resident LSD radix sort in shared memory (k_refine_radix)
+//                             > 8192      one CTA, LSD radix passes through HBM        (k_refine_large)
+//   4. shortcuts            tandem repeats resolved in one step (2d, k_resolve_periodic); long non-tandem repeats
+//                           followed to their end by position-indexed scans while refinement stalls (2e, k_rep_*).
+//   5. last column          bwt[k] = T[(sa[k]-1) mod n]; origPtr = rank of rotation 0 (k_bwt_out, k_power_origptr).
 //
 // A segment that survives to depth >= n holds equal rotations: the block is an exact
 // power u^q; q is recorded in power_q[b] (the BWT bytes do not depend on their order).
