@@ -52,18 +52,24 @@ def make_input(workload, n, rank=0):
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line), through
-    NVML in-process and at a rate that adapts to what a query costs: a query takes the driver's lock, and on some
-    boxes spawning nvidia-smi (or polling NVML every few ms) stretched the timed step by 10 % to 4x."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line) through NVML,
+    at a rate that adapts to what a query costs: a query takes the driver's lock, and on some boxes spawning
+    nvidia-smi (or polling NVML every few ms) stretched the timed step by 10 % to 4x."""
 
-    def __init__(self, index, count=1):
+    def __init__(self, index, count=1, mode=None):
         self.rows = []
         self.stop = False
         self.index = index
-        self.count = count            # GPUs index .. index+count-1 are sampled (rank 0 samples every local GPU)
+        self.count = count            # GPUs index .. index+count-1 are sampled
         self.how = "nvml"
         self.query_ms = []
+        # proc (default): a small helper process polls NVML (0.02 ms per query, no effect on the step).  thread: a sampler
+        # thread in this process -- its queries sometimes waited 20-290 ms behind the process's own CUDA calls and stalled
+        # one timed step in three at N = 2 (9.1 instead of 11.3 GB/s).  inline: the timed loop polls between steps.
+        self.mode = mode or os.environ.get("BENCH_CLOCKS", "proc")
         self.th = threading.Thread(target=self.run, daemon=True)
+        self.proc = None
+        self._nv = None
 
     def _run_nvml(self):
         import pynvml as nv
@@ -117,7 +123,68 @@ class ClockSampler:
             self.ready.set()
             self._run_smi()
 
+    def _handles(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        hs = []
+        for k in range(self.index, self.index + self.count):
+            idx = k
+            if vis:
+                try:
+                    idx = int(vis.split(",")[k])
+                except Exception:  # noqa: BLE001
+                    pass
+            hs.append(nv.nvmlDeviceGetHandleByIndex(idx))
+        return nv, hs
+
+    def poll(self):
+        """inline mode: one sample, taken by the caller's thread between two steps of the timed region"""
+        if self.mode != "inline" or self._nv is None:
+            return
+        nv, hs, mx = self._nv
+        t0 = time.perf_counter()
+        for h, m in zip(hs, mx):
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            row = [str(sm), str(m)] + ["Not Active"] * 4
+            for bit, k in ((nv.nvmlClocksEventReasonHwSlowdown, 0), (nv.nvmlClocksEventReasonHwThermalSlowdown, 1),
+                           (nv.nvmlClocksEventReasonSwThermalSlowdown, 2), (nv.nvmlClocksEventReasonSwPowerCap, 3)):
+                if r & bit:
+                    row[2 + k] = "Active"
+            self.rows.append(row)
+        self.query_ms.append((time.perf_counter() - t0) * 1e3)
+
     def __enter__(self):
+        if self.mode == "inline":
+            try:
+                nv, hs = self._handles()
+                self._nv = (nv, hs, [nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM) for h in hs])
+                self.how = "nvml, sampled by the timing thread between steps"
+                return self
+            except Exception:  # noqa: BLE001
+                self.mode = "thread"
+        if self.mode == "proc":
+            code = ("import sys,time,pynvml as nv\nnv.nvmlInit()\nh=nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))\n"
+                    "m=nv.nvmlDeviceGetMaxClockInfo(h,nv.NVML_CLOCK_SM)\nprint('ready',flush=True)\n"
+                    "while True:\n t=time.perf_counter()\n s=nv.nvmlDeviceGetClockInfo(h,nv.NVML_CLOCK_SM)\n"
+                    " r=nv.nvmlDeviceGetCurrentClocksEventReasons(h)\n d=(time.perf_counter()-t)*1e3\n"
+                    " print(s,m,r,d,flush=True)\n time.sleep(max(0.1,30*d/1e3))\n")
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except Exception:  # noqa: BLE001
+                    pass
+            try:
+                self.proc = subprocess.Popen([sys.executable, "-c", code, str(idx)], stdout=subprocess.PIPE, text=True)
+                self.proc.stdout.readline()
+                self.how = "nvml, helper process"
+                return self
+            except Exception:  # noqa: BLE001
+                self.proc = None
+                self.mode = "thread"
         self.ready = threading.Event()
         self.th.start()
         self.ready.wait(timeout=10)          # NVML initialisation stays outside the timed region
@@ -125,6 +192,21 @@ class ClockSampler:
 
     def __exit__(self, *a):
         self.stop = True
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:  # noqa: BLE001
+                out = ""
+            for ln in out.splitlines():
+                f = ln.split()
+                if len(f) == 4:
+                    r = int(f[2])
+                    self.rows.append([f[0], f[1]] + ["Active" if r & b else "Not Active" for b in (0x8, 0x40, 0x20, 0x4)])
+                    self.query_ms.append(float(f[3]))
+            return
+        if self.mode == "inline":
+            return
         self.th.join(timeout=6)
 
     def summary(self):
@@ -166,6 +248,17 @@ def cpu_reference_rate(data, level, threads, seconds_budget, sample_bytes):
     return per * threads / dt / 1e6, kind, f"{per * threads} B prefix of the workload as {threads} independent slice(s), -{level}, one pass, {dt:.1f} s"
 
 
+def merge_clocks(per_rank):
+    """One clocks object for the node: the lowest per-GPU median SM clock, every throttle reason any GPU reported."""
+    ok = [c for c in per_rank if c and c.get("sm_mhz") is not None]
+    if not ok:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+    reasons = sorted({r for c in ok for r in c.get("reasons", [])})
+    return {"sm_mhz": min(c["sm_mhz"] for c in ok), "sm_max_mhz": max(c["sm_max_mhz"] for c in ok), "reasons": reasons,
+            "samples": sum(c.get("samples", 0) for c in ok), "source": ok[0].get("source"),
+            "query_ms": max((c.get("query_ms") or 0.0) for c in ok), "per_gpu_sm_mhz": [c["sm_mhz"] for c in ok]}
+
+
 def sharded_bench(args, torch, dist, B, rank, world, local_rank, dev, data, n, metric, config):
     """N > 1: ONE .bz2 stream, sharded by block across the ranks (bzip2_b200/sharding.py): every rank scans
     its shard (+ halo) for chunk ends, the block-boundary chain is one integer handed rank to rank, every rank
@@ -203,7 +296,7 @@ def sharded_bench(args, torch, dist, B, rank, world, local_rank, dev, data, n, m
 
     per_step = []          # this rank's host-side time of every timed step (diagnostic)
 
-    def timed(resident, steps):
+    def timed(resident, steps, poll=None):
         """K steps bracketed by barrier + synchronize, timed on the device; returns (max over ranks in s, last result)."""
         barrier()
         ev0.record()
@@ -213,6 +306,8 @@ def sharded_bench(args, torch, dist, B, rank, world, local_rank, dev, data, n, m
             t1 = time.perf_counter()
             res = one(resident)
             per_step.append(round((time.perf_counter() - t1) * 1e3, 2))
+            if poll is not None:
+                poll()
         ev1.record()
         barrier()
         wall = time.perf_counter() - t0
@@ -222,10 +317,11 @@ def sharded_bench(args, torch, dist, B, rank, world, local_rank, dev, data, n, m
 
     for _ in range(args.warmup):
         out, info = one(True)
-    import contextlib
-    # rank 0 samples every GPU of the node; one sampler per rank only multiplies the driver-lock traffic
-    with (ClockSampler(0, world) if rank == 0 else contextlib.nullcontext()) as clk:
-        dev_s, wall_s, (out, info) = timed(True, args.steps)
+    # every rank samples its own GPU (helper process, see ClockSampler); rank 0 merges the summaries
+    with ClockSampler(local_rank, 1) as clk:
+        dev_s, wall_s, (out, info) = timed(True, args.steps, clk.poll)
+    clk_all = [None] * world
+    dist.all_gather_object(clk_all, clk.summary())
     ms_per_step = dev_s / args.steps * 1e3
     resident_steps = list(per_step)
     proto = [None] * world
@@ -266,7 +362,7 @@ def sharded_bench(args, torch, dist, B, rank, world, local_rank, dev, data, n, m
         config["workload"] += f"; ONE stream of {world} x {args.mb} MB sharded by block, 64 MiB halo per rank"
         line = {"metric": metric, "value": round(value, 2), "unit": "MB/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config, "clocks": clk.summary(),
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config, "clocks": merge_clocks(clk_all),
                 "e2e": e2e, "gpu_launches": int(st.kernel_launches), "roofline": roof, "cpu_baseline": None,
                 "out_bytes": int(info["total_bytes"]), "blocks_rank0": int(st.n_blocks),
                 "wall_ms_per_step": round(wall_s / args.steps * 1e3, 3), "protocol_ms_per_rank": proto, "step_ms_rank0": resident_steps}
