@@ -45,6 +45,9 @@ def stream_cases():
     # block-fill corner: block fills exactly one byte before the end (bzlib.c:276-308)
     yield "tailmerge_L1", (np.arange(99981 + 1, dtype=np.uint32) % 251).astype(np.uint8), 1
     yield "tailmerge2_L1", (np.arange(99981 + 2, dtype=np.uint32) % 251).astype(np.uint8), 1
+    # long non-tandem repeats (stage 2, repeat passes)
+    for name, d in S.long_repeat_cases():
+        yield "rep_" + name + "_L9", d, 9
 
 
 def power_cases():

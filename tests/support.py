@@ -307,3 +307,23 @@ def power_stream_cases():
     yield "aab_2M_L9", gen_tile(2_000_000, b"aab"), 9
     yield "aab_500k_L1", gen_tile(500_000, b"aab"), 1
     yield "period7_400k_L1", gen_tile(400_000, b"1234567"), 1
+
+
+def long_repeat_cases():
+    """Inputs with long NON-tandem repeats (a copy of the same data hundreds of kB further on): the shapes the
+    repeat passes of stage 2 (2e) exist for.  (name, uint8 array); seeded, so they double as golden stream cases."""
+    rng = np.random.default_rng(5)
+    r300 = rng.integers(0, 256, 300_000, dtype=np.uint8)
+    txt = gen_text(260_000, seed=9)
+    edited = txt.copy()
+    edited[100_000] ^= 1                                     # second copy differs in one byte
+    binary = np.frombuffer(open(os.path.join(GOLDEN, "sample1.ref"), "rb").read() + open(os.path.join(GOLDEN, "sample2.ref"), "rb").read(), np.uint8)
+    few = rng.integers(0, 4, 5_000, dtype=np.uint8) + 65
+    return [
+        ("random300k_x3", np.resize(r300, 2_000_000)),                      # every rotation has a twin 300 kB further on
+        ("random130k_x7", np.resize(r300[:130_000], 1_700_000)),            # up to seven copies per block: several keys per visit
+        ("text_twice_edited", np.concatenate([txt, edited, txt[:150_000]])),
+        ("binary_tiled", np.resize(binary, 1_900_000)),                     # the C4 binary third
+        ("period5000_4sym", np.resize(few, 1_500_000)),
+        ("random_then_copy_shifted", np.concatenate([r300[:200_000], few, r300[:200_000], r300[50_000:250_000]])),
+    ]

@@ -193,32 +193,14 @@ def test_periodic_segments_resolve_in_one_step(engine_for):
     assert eng.stats.bwt_rounds <= 12
 
 
-def _long_repeat_cases():
-    rng = np.random.default_rng(5)
-    r300 = rng.integers(0, 256, 300_000, dtype=np.uint8)
-    txt = S.gen_text(260_000, seed=9)
-    edited = txt.copy()
-    edited[100_000] ^= 1                                     # second copy differs in one byte
-    binary = np.frombuffer(open(os.path.join(G, "sample1.ref"), "rb").read() + open(os.path.join(G, "sample2.ref"), "rb").read(), np.uint8)
-    few = rng.integers(0, 4, 5_000, dtype=np.uint8) + 65
-    return [
-        ("random300k_x3", np.resize(r300, 2_000_000)),                      # every rotation has a twin 300 kB further on
-        ("random130k_x7", np.resize(r300[:130_000], 1_700_000)),            # up to seven copies per block: several keys per visit
-        ("text_twice_edited", np.concatenate([txt, edited, txt[:150_000]])),
-        ("binary_tiled", np.resize(binary, 1_900_000)),                     # the C4 binary third
-        ("period5000_4sym", np.resize(few, 1_500_000)),
-        ("random_then_copy_shifted", np.concatenate([r300[:200_000], few, r300[:200_000], r300[50_000:250_000]])),
-    ]
-
-
 def test_long_repeats_follow_chains(engine_for):
     """Non-tandem repeats (stage2 2e): same bytes as the oracle, and the rounds do not grow with log2(repeat length)."""
     eng = engine_for(9)
-    for name, d in _long_repeat_cases():
+    for name, d in S.long_repeat_cases():
         assert eng.compress(d) == S.orc_compress(d, 9), name
         if name in ("random300k_x3", "binary_tiled"):
             assert eng.stats.bwt_rounds <= 9 * ((d.size + 899_980) // 899_981), (name, eng.stats.bwt_rounds)
-    d = _long_repeat_cases()[0][1]
+    d = S.long_repeat_cases()[0][1]
     assert engine_for(3).compress(d) == S.orc_compress(d, 3)
 
 
@@ -229,7 +211,7 @@ def test_chains_from_the_first_doubling_round(monkeypatch):
     monkeypatch.setenv("BZ2_B200_CHAIN", "2")
     eng = B.Engine(level=9)
     try:
-        cases = _long_repeat_cases() + [("text", S.gen_text(2_000_000)), ("p1000", S.gen_period1000(1_000_000)),
+        cases = S.long_repeat_cases() + [("text", S.gen_text(2_000_000)), ("p1000", S.gen_period1000(1_000_000)),
                                         ("aab", S.gen_tile(1_000_000, b"aab")), ("mixed", S.gen_mixed(2_000_000, seg=1 << 17)),
                                         ("runs", S.gen_runs(3_000_000))]
         for name, d in cases:
