@@ -178,11 +178,15 @@ class ClockSampler:
                 except Exception:  # noqa: BLE001
                     pass
             try:
-                self.proc = subprocess.Popen([sys.executable, "-c", code, str(idx)], stdout=subprocess.PIPE, text=True)
-                self.proc.stdout.readline()
+                self.proc = subprocess.Popen([sys.executable, "-c", code, str(idx)], stdout=subprocess.PIPE,
+                                             stderr=subprocess.DEVNULL, text=True)
+                if self.proc.stdout.readline().strip() != "ready":      # NVML did not come up in the helper
+                    raise RuntimeError("clock helper failed")
                 self.how = "nvml, helper process"
                 return self
             except Exception:  # noqa: BLE001
+                if self.proc is not None:
+                    self.proc.kill()
                 self.proc = None
                 self.mode = "thread"
         self.ready = threading.Event()
