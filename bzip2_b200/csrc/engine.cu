@@ -92,7 +92,8 @@ static void engine_free(EngineFull* e)
                    e->mtf_summary, e->mtf_tilemeta, e->mtf_tilecnt, e->mtf_mode, e->sel, e->hlen, e->hfreq, e->hcode, e->grpbits,
                    e->pre, e->prebits, e->ngroups, e->d_in, e->d_out,
                    e->bt.X, e->bt.P, e->bt.crc, e->bt.origptr, e->bt.power_q, e->bt.inuse, e->bt.ninuse, e->bt.nmtf,
-                   e->bt.mtffreq, e->bt.bits, e->bt.bitoff, e->lists.counts[0], e->lists.counts[1] };
+                   e->bt.mtffreq, e->bt.bits, e->bt.bitoff, e->lists.counts[0], e->lists.counts[1],
+                   e->tie_tmp, e->bt.tie_flag, e->bt.tie_lo };
    for (void* p : dev) if (p) cudaFree(p);
    for (int w = 0; w < 2; w++) {
       for (int c = 0; c < N_SMALL_CLASSES; c++) if (e->lists.small_items[w][c]) cudaFree(e->lists.small_items[w][c]);
@@ -147,6 +148,8 @@ static int engine_new(EngineFull** out, int device, int level, size_t window_byt
       e->s2_streams = ss ? (u32)atoi(ss) : 1;
       const char* ch = getenv("BZ2_B200_CHAIN");
       e->chain = ch ? (u32)atoi(ch) : 1;
+      const char* tf2 = getenv("BZ2_B200_TIE_FORCE");
+      e->tie_force = tf2 ? (u32)atoi(tf2) : 0;
       const char* cr = getenv("BZ2_B200_CHAIN_MIN_ROUND");
       e->chain_min_round = cr ? (u32)atoi(cr) : 2;
    }
@@ -188,6 +191,7 @@ static int engine_new(EngineFull** out, int device, int level, size_t window_byt
       ALLOC(e->code, B * 256); ALLOC(e->kk, B); ALLOC(e->nbins, B); ALLOC(e->hh, B); ALLOC(e->kbits, B); ALLOC(e->ksym, B);
       ALLOC(e->K, E + 64); ALLOC(e->kscrA, E + 64); ALLOC(e->kscrB, E + 64);
       ALLOC(e->blockmap, E / 4096 + 4);
+      ALLOC(e->tie_tmp, B * 256); ALLOC(e->bt.tie_flag, B); ALLOC(e->bt.tie_lo, B);
       ALLOC(e->tile_len, ntiles); ALLOC(e->tile_ext, ntiles); ALLOC(e->tile_carry, ntiles);
       ALLOC(e->tile_size, ntiles); ALLOC(e->tile_base, ntiles);
       ALLOC(e->s1_scalars, 16);

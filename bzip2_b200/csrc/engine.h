@@ -49,6 +49,8 @@ struct BlockTables {                        // per-window block metadata (device
    u32* crc;        // [nb]   finalised block CRC
    u32* origptr;    // [nb]
    u32* power_q;    // [nb]   0, or q if the block is an exact power u^q
+   u32* tie_flag;   // [nb]   1: exact power whose origPtr needs the tie-order replay (stage2_tie.cu)
+   u32* tie_lo;     // [nb]   start of rotation 0's tie group (kept only when the replay is forced)
    u8*  inuse;      // [nb*256]
    u32* ninuse;     // [nb]
    u32* nmtf;       // [nb]
@@ -79,6 +81,7 @@ int scan_boundary(ScanState* s, u32 start, u32 limit, u32 tail_merge, u32* bound
 int stage1_run(Engine* e, const u8* d_in, u32 W, bool is_final, bool tail_merge, u32* nb_out, u32* consumed_out, u32* enc_total_out);
 int stage2_init();
 int stage2_run(Engine* e, u32 nb, u32 E);
+int stage2_power_origptr(Engine* e, u32 b0, u32 g);
 int stage3_run(Engine* e, u32 nb, u32 E);
 int stage4_run(Engine* e, u32 nb, u32 E, u8* d_out, u64 origin_bit, u64 start_bit, u64* end_bit_out);
 int put_bits_device(Engine* e, u8* d_out, u64 origin_bit, u64 bitpos, u64 value, int nbits);
@@ -122,6 +125,8 @@ struct Engine {
    cudaStream_t aux[3];    // side streams of the BWT rounds
    cudaEvent_t ev_fork, ev_join[3];
    u32 *blockmap;          // [enc_cap/4096 + 2] block id of each 4 KiB chunk of enc
+   u32 *tie_tmp;           // [blk_cap*256] side buffers of the tie-order replay
+   u32 tie_force;          // BZ2_B200_TIE_FORCE=1: replay every exact-power block (tests: closed form == replay)
    SegLists lists;
    BlockTables bt;
 

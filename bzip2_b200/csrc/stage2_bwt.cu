@@ -21,7 +21,7 @@
 //                             > 8192      one CTA, LSD radix passes through HBM        (k_refine_large)
 //   4. shortcuts            tandem repeats resolved in one step (2d, k_resolve_periodic); long non-tandem repeats
 //                           followed to their end by position-indexed scans while refinement stalls (2e, k_rep_*).
-//   5. last column          bwt[k] = T[(sa[k]-1) mod n]; origPtr = rank of rotation 0 (k_bwt_out, k_power_origptr).
+//   5. last column          bwt[k] = T[(sa[k]-1) mod n]; origPtr = rank of rotation 0 (k_bwt_out; exact powers: stage2_tie.cu).
 //
 // A segment that survives to depth >= n holds equal rotations: the block is an exact
 // power u^q; q is recorded in power_q[b] (the BWT bytes do not depend on their order).
@@ -1311,56 +1311,6 @@ __global__ void __launch_bounds__(KG_THREADS) k_bwt_out(S2Params p, u8* bwt, u32
    }
 }
 
-// origPtr on exact powers u^q: the reference's value is lo + g, g an artefact of divsufsort's internal order
-// (SURVEY 7#1).  For units with a single B* suffix -- one local-maximum run, cyclically: constant data after
-// RLE1, "aab"-like periods -- g depends on the parity of |u| and on q only (measured on the reference, pinned by
-// tests/golden/origptr_powers.json; the CPU statement is oracle/bz2_oracle.c orc_power_offset).  One warp per block.
-__global__ void __launch_bounds__(32) k_power_origptr(S2Params p, u32* origptr)
-{
-   const u32 b = p.b0 + blockIdx.x;
-   const u32 q = p.power_q[b];
-   if (q < 2) return;
-   const u32 xb = p.X[b], n = p.X[b + 1] - xb;
-   if (n % q) return;
-   const u32 per = n / q;
-   if (per == 1) return;                                   // all-equal block: origPtr stays 0
-   const u8* T = p.T + xb;
-   const u32 l = lane_id();
-   // every lane scans a contiguous chunk of the unit's step signs and summarises it as
-   // (first non-zero sign, last non-zero sign, number of +- transitions inside)
-   const u32 chunk = (per + 31) / 32;
-   const u32 lo = min(per, l * chunk), hi = min(per, lo + chunk);
-   int first = 0, last = 0; u32 cnt = 0;
-   for (u32 i = lo; i < hi; i++) {
-      const int a = T[i], c = T[(i + 1 == per) ? 0 : i + 1];
-      const int sgn = (c > a) - (c < a);
-      if (!sgn) continue;
-      if (!first) first = sgn;
-      if (last > 0 && sgn < 0) cnt++;
-      last = sgn;
-   }
-   // lane 0 stitches the 32 summaries in order, then across the wrap
-   u32 peaks = 0; int run_last = 0, run_first = 0;
-   for (int k = 0; k < 32; k++) {
-      const int f = __shfl_sync(FULL, first, k), la = __shfl_sync(FULL, last, k);
-      const u32 c = __shfl_sync(FULL, cnt, k);
-      peaks += c;
-      if (f) {
-         if (run_last > 0 && f < 0) peaks++;
-         if (!run_first) run_first = f;
-         run_last = la;
-      }
-   }
-   if (run_last > 0 && run_first < 0) peaks++;
-   if (l != 0 || peaks != 1) return;
-   u32 g;
-   if ((per & 1u) == 0 || q <= 9) g = 1;
-   else if (q <= 1025) g = (q & 1u) ? (q + 1) / 2 : 0;
-   else if (q <= 1027) g = 0;
-   else g = 513;
-   origptr[b] += g;
-}
-
 // --------------------------------------------------------------------------------------
 static ListsDev lists_dev(Engine* e, int which)
 {
@@ -1621,7 +1571,7 @@ int stage2_run(Engine* e, u32 nb, u32 E)
          cur = nxt;
       }
       k_bwt_out<<<gtiles, KG_THREADS, 0, st>>>(p, e->bwt, e->bt.origptr);                       BZ_KCHECK(e);
-      k_power_origptr<<<g, 32, 0, st>>>(p, e->bt.origptr);                                      BZ_KCHECK(e);
+      { const int rc = stage2_power_origptr(e, b0, g); if (rc) return rc; }                      // exact powers (stage2_tie.cu)
    }
    return 0;
 }

@@ -93,7 +93,9 @@ int32_t orc_rle1_emit(const uint8_t* in, uint64_t begin, uint64_t end,
 /* Contract of BZ2_blockSort (blocksort.c:1520-1545): rotations of the block
  * in lexicographic order; output byte k is the byte preceding rotation k;
  * origPtr is the rank of rotation 0.  Restated with Manber-Myers prefix
- * doubling over cyclic ranks (not the reference's divsufsort). */
+ * doubling over cyclic ranks (not the reference's divsufsort); when the block
+ * is an exact power the tie among equal rotations is settled as the reference
+ * settles it (tie_order.c). */
 int32_t orc_bwt(const uint8_t* blk, int32_t n, uint8_t* bwt, int32_t* orig_ptr)
 {
    if (n <= 0) return 0;
@@ -137,37 +139,10 @@ int32_t orc_bwt(const uint8_t* blk, int32_t n, uint8_t* bwt, int32_t* orig_ptr)
    *orig_ptr = rk[0];
    int32_t q = n / groups;
    free(sa); free(sb); free(rk); free(rn); free(pos);
+   /* exact power: rk[0] is the start of rotation 0's tie group; the reference's value is that plus
+    * the trace of its sorter's tie order (oracle/tie_order.c) */
+   if (q > 1) *orig_ptr += orc_tie_offset(blk, n, q);
    return q;
-}
-
-/* origPtr on exact powers.  blk = u^q (u primitive, p = n/q, q >= 2): the q copies of a rotation are equal and
- * the reference's origPtr = lo + g is whichever of them divsufsort happens to leave where.  When u
- * has exactly one B* suffix (one local-maximum run, cyclically) all B* suffixes of the block are
- * indistinguishable and g is a function of p's parity and q alone -- the traces of ss_mintrosort's pivot swap
- * per substring level (blocksort.c:349-351), its 1024-element chunking (:36, :637-652) and the last-suffix
- * re-insertion (:654-663).  The rule below was measured on the reference (1,900 random single-peak (u, q)
- * and every q in 2..1060) and is pinned by tests/golden/origptr_powers.json.  Units with several B* suffixes
- * follow family-specific variants of the same traces; for them -1 is returned and callers keep lo. */
-int32_t orc_power_offset(const uint8_t* blk, int32_t n, int32_t q)
-{
-   if (q < 2 || n % q) return -1;
-   const int32_t p = n / q;
-   if (p == 1) return 0;                           /* all-equal block: origPtr 0 (blocksort.c:1349) */
-   int first = 0, last = 0, peaks = 0;
-   for (int32_t i = 0; i < p; i++) {
-      const int a = blk[i], b = blk[(i + 1) % p];
-      const int sgn = (b > a) - (b < a);
-      if (!sgn) continue;
-      if (!first) first = sgn;
-      if (last > 0 && sgn < 0) peaks++;
-      last = sgn;
-   }
-   if (last > 0 && first < 0) peaks++;             /* the transition across the wrap */
-   if (peaks != 1) return -1;
-   if ((p & 1) == 0 || q <= 9) return 1;
-   if (q <= 1025) return (q & 1) ? (q + 1) / 2 : 0;
-   if (q <= 1027) return 0;
-   return 513;
 }
 
 /* ------------------------------------------------------------------ MTF -- */
@@ -400,7 +375,7 @@ int64_t orc_compress_ex(const uint8_t* in, uint64_t n, int level, int tail_merge
       int32_t nblock = orc_rle1_emit(in, blocks[b].in_begin, blocks[b].in_end, blk, in_use);
       if (nblock != blocks[b].nblock) { free(blocks); free(blk); free(bwt); free(mtfv); return -3; }
       const int32_t q = orc_bwt(blk, nblock, bwt, &op);
-      if (q > 1) { const int32_t g = orc_power_offset(blk, nblock, q); if (g > 0) op += g; }
+      (void)q;
       if (force_orig_ptr && force_orig_ptr[b] >= 0) op = force_orig_ptr[b];
       int32_t nm = orc_mtf(bwt, nblock, in_use, mtfv, freq, &nu);
       comb = ((comb << 1) | (comb >> 31)) ^ blocks[b].crc;                                /* compress.c:826-828 */

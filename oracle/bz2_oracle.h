@@ -13,11 +13,10 @@
  * Parity pin: validated against (a) the reference's own known-answer vectors
  * sample{1,2,3}.ref -> sample{1,2,3}.bz2 (Makefile:58-66) and (b) the reference
  * itself compiled as oracle/_ref/libbz2_ref.so (differential fuzz in
- * tests/test_oracle_vs_ref.py).  Known limit: on blocks that are an exact power
- * u^q (q >= 2) the reference's origPtr is an artefact of divsufsort's internal
- * order.  It is reproduced for units with a single B*
- * suffix (constant data, "aab"-like periods; orc_power_offset()), not for units
- * with several.
+ * tests/test_oracle_vs_ref.py, tests/test_tie_order.py).  On blocks that are an
+ * exact power u^q (q >= 2) the reference's origPtr is an artefact of
+ * divsufsort's internal order; tie_order.c replays the
+ * part of the reference's sorter that decides it, so origPtr is exact there too.
  */
 #ifndef BZ2_ORACLE_H
 #define BZ2_ORACLE_H
@@ -46,14 +45,18 @@ int32_t orc_rle1_emit(const uint8_t* in, uint64_t begin, uint64_t end,
                       uint8_t* out, uint8_t* in_use);
 
 /* Cyclic-rotation BWT (blocksort.c:1534-1545 contract).  Returns the period
- * class count: 1 if all rotations are distinct, q >= 2 if blk == u^q.  When
- * q >= 2, *orig_ptr is the SMALLEST rank among the q equal copies (lo); the
- * reference's value is lo + g with g in [0,q). */
+ * class count: 1 if all rotations are distinct, q >= 2 if blk == u^q.
+ * *orig_ptr is the reference's value in both cases: when q >= 2 it is
+ * lo + orc_tie_offset(), lo being the smallest rank among the q equal copies
+ * of rotation 0. */
 int32_t orc_bwt(const uint8_t* blk, int32_t n, uint8_t* bwt, int32_t* orig_ptr);
 
-/* g of the reference's origPtr = lo + g on an exact power u^q whose unit has a single B* suffix (measured
- * rule, see the definition); -1 when the unit has several B* suffixes (origPtr stays lo there). */
-int32_t orc_power_offset(const uint8_t* blk, int32_t n, int32_t q);
+/* Exact power blk = u^q (q >= 2): g in [0,q) with origPtr_ref = lo + g, obtained by replaying the
+ * reference's B*-suffix sort (tie_order.c; blocksort.c:1316-1401).  orc_bstar_ranks is the replay
+ * itself: work = n + 256 ints, bstar = 65536 ints, T[n] == T[0]; returns the number m of B*
+ * suffixes and leaves their ranks in work[m .. 2m). */
+int32_t orc_tie_offset(const uint8_t* blk, int32_t n, int32_t q);
+int32_t orc_bstar_ranks(const uint8_t* T, int32_t n, int32_t* work, int32_t* bstar);
 
 /* MTF + zero-run coding (compress.c:93-229). Returns nMTF. */
 int32_t orc_mtf(const uint8_t* bwt, int32_t n, const uint8_t* in_use,

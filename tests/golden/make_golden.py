@@ -6,6 +6,8 @@ Run in the authoring container only (needs /root/reference to have been compiled
   sample{1,2,3}.ref / .bz2   the reference's own known-answer vectors (Makefile:58-66), copied verbatim
   streams.json               sha256 + length of the reference's output for seeded synthetic inputs
   origptr_powers.json        the reference's origPtr on exact-power blocks u^q
+  powers_random.json         240 seeded random (u, q): sha256 of the reference's stream at -1 and -9, and the
+                             reference's origPtr when the input is a single block at -9
 """
 import hashlib
 import json
@@ -65,6 +67,30 @@ def power_cases():
     yield b"cab", 299993
 
 
+def random_power_params():
+    """(seed, p, alpha, q).  Small: one block at both levels.  Divisor periods of nblockMAX(-1) = 99,981 =
+    27*7*529: every full block at -1 is an exact power.  Large: one block of up to 899,981 bytes at -9."""
+    import random
+    rng = random.Random(20261018)
+    out = []
+    for k in range(130):
+        p = rng.randint(2, 40)
+        alpha = rng.choice([2, 3, 4, 6, 256])
+        q = rng.choice([2, 3, 9, 10, 11, 100, 513, 1024, 1025, 1026, 1027, 1028, 2049, rng.randint(2, 4000)])
+        q = max(2, min(q, 99_000 // p))
+        out.append((1000 + k, p, alpha, q))
+    for k in range(80):
+        p = rng.choice([3, 7, 9, 21, 23, 27, 63, 69, 161, 189, 207, 483, 529, 621, 1587, 3703])
+        alpha = rng.choice([3, 4, 5, 26, 256])
+        out.append((2000 + k, p, alpha, rng.randint(2 * 99_981 // p, 4 * 99_981 // p) + 1))
+    for k in range(30):
+        p = rng.choice([rng.randint(41, 3000), rng.randint(3000, 150_000), rng.randint(150_000, 449_990)])
+        alpha = rng.choice([2, 4, 256])
+        qmax = 899_981 // p
+        out.append((3000 + k, p, alpha, max(2, rng.choice([2, 3, qmax, rng.randint(2, qmax)]))))
+    return out
+
+
 def main():
     streams = {}
     for name, data, level in stream_cases():
@@ -80,6 +106,18 @@ def main():
         powers.append({"unit": u.decode("latin-1"), "q": q, "orig_ptr": int(op)})
     json.dump(powers, open(os.path.join(HERE, "origptr_powers.json"), "w"), indent=0)
     print(len(powers), "power cases")
+    rnd = []
+    for seed, p, alpha, q in random_power_params():
+        d = S.random_power_case(seed, p, alpha, q)
+        rec = {"seed": seed, "p": p, "alpha": alpha, "q": q}
+        for level in (1, 9):
+            rec[f"sha_L{level}"] = hashlib.sha256(S.ref_compress(d, level)).hexdigest()
+        recs = S.ref_trace(d, 9)[0]
+        if len(recs) == 1:                                  # one block at -9: the reference's origPtr for it
+            rec["orig_ptr"] = int(recs[0].orig_ptr)
+        rnd.append(rec)
+    json.dump(rnd, open(os.path.join(HERE, "powers_random.json"), "w"), indent=0)
+    print(len(rnd), "random power cases,", sum("orig_ptr" in r for r in rnd), "with origPtr")
 
 
 if __name__ == "__main__":

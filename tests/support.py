@@ -45,8 +45,8 @@ def oracle():
     lib.orc_rle1_emit.argtypes = [u8p, C.c_uint64, C.c_uint64, u8p, u8p]
     lib.orc_bwt.restype = C.c_int32
     lib.orc_bwt.argtypes = [u8p, C.c_int32, u8p, C.POINTER(C.c_int32)]
-    lib.orc_power_offset.restype = C.c_int32
-    lib.orc_power_offset.argtypes = [u8p, C.c_int32, C.c_int32]
+    lib.orc_tie_offset.restype = C.c_int32
+    lib.orc_tie_offset.argtypes = [u8p, C.c_int32, C.c_int32]
     lib.orc_mtf.restype = C.c_int32
     lib.orc_mtf.argtypes = [u8p, C.c_int32, u8p, C.POINTER(C.c_uint16), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.orc_make_code_lengths.restype = None
@@ -174,10 +174,10 @@ def orc_bwt(block):
     return out, op.value, q
 
 
-def orc_power_offset(block, q):
-    """g with origPtr_ref = lo + g for an exact power block (single-B* units), or -1."""
+def orc_tie_offset(block, q):
+    """g with origPtr_ref = lo + g for an exact power block u^q (oracle/tie_order.c)."""
     a = as_u8(block)
-    return int(oracle().orc_power_offset(_buf(a), a.size, q))
+    return int(oracle().orc_tie_offset(_buf(a), a.size, q))
 
 
 def orc_mtf(bwt, inuse):
@@ -300,13 +300,28 @@ def gen_c4(n, seg=64 << 20):
 
 
 def power_stream_cases():
-    """Inputs whose blocks are exact powers of a unit with a single B* suffix (golden streams minted from the reference)."""
+    """Inputs whose blocks are exact powers u^q (golden streams minted from the reference).  The first six have
+    units with a single B* suffix (closed form on the GPU), the rest several (tie-order replay)."""
     yield "zeros_2M_L9", np.zeros(2_000_000, np.uint8), 9
     yield "zeros_700k_L1", np.zeros(700_000, np.uint8), 1
     yield "ff_1M_L5", np.full(1_000_000, 255, np.uint8), 5
     yield "aab_2M_L9", gen_tile(2_000_000, b"aab"), 9
     yield "aab_500k_L1", gen_tile(500_000, b"aab"), 1
     yield "period7_400k_L1", gen_tile(400_000, b"1234567"), 1
+    rec7 = gen_tile(420_000, b"ab\ncd\n.")                  # 7-byte records: every full block at -1 is (rec)^14283
+    yield "rec7_420k_L1", rec7, 1
+    yield "rec7_420k_L5", rec7, 5
+    yield "rec7_420k_L9", rec7, 9
+    yield "abcabd_600k_L2", gen_tile(600_000, b"abcabd"), 2
+    yield "aabb_900k_L3", gen_tile(900_000, b"aabb"), 3
+    yield "abcdcb_1M_L1", gen_tile(1_000_000, b"abcdcb"), 1
+    yield "rec21_350k_L1", gen_tile(350_000, b"id,name,value\n1,ab,2\n"), 1
+
+
+def random_power_case(seed, p, alpha, q):
+    """u = p seeded bytes over an alphabet of `alpha`, tiled q times (tests/golden/powers_random.json)."""
+    u = gen_random(p, seed=seed).astype(np.uint32) % alpha + (48 if alpha < 200 else 0)
+    return np.tile(u.astype(np.uint8), q)
 
 
 def long_repeat_cases():

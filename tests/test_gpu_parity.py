@@ -88,14 +88,8 @@ def test_stage_outputs(engine_for, gen, n, level):
     b"a" * 259 + b"b", b"a" * 510 + b"b", b"a" * 600, bytes(range(256)), bytes(range(256)) * 3,
 ])
 def test_tiny_inputs(data):
-    # exact-power inputs only need the same bytes up to origPtr; the oracle returns the tie group start
     got = B.compress(data, 9)
-    exp = S.orc_compress(data, 9)
-    if len(data) and S.orc_bwt(np.frombuffer(data, np.uint8) if len(data) < 4 else S.orc_rle1_emit(data, 0, len(data))[0])[2] > 1:
-        assert len(got) == len(exp)
-        assert bz2.decompress(got) == data
-    else:
-        assert got == exp
+    assert got == S.orc_compress(data, 9)
     if data:
         assert bz2.decompress(got) == data
 
@@ -135,9 +129,7 @@ def test_fuzz_small(engine_for):
         else:
             d = S.gen_text(n, seed=it + 1)
         got = eng.compress(d)
-        enc, _ = S.orc_rle1_emit(d, 0, d.size)
-        if S.orc_bwt(enc)[2] == 1:
-            assert got == S.orc_compress(d, 9), (it, mode, n)
+        assert got == S.orc_compress(d, 9), (it, mode, n)
         assert bz2.decompress(got) == d.tobytes(), (it, mode, n)
 
 
@@ -148,31 +140,66 @@ def test_all_levels(engine_for):
 
 
 def test_exact_power_blocks_bwt(engine_for):
-    """Equal rotations: BWT bytes are canonical, the block is flagged with its multiplicity q, and origPtr lies
-    in the tie group -- at the reference's own position inside it when the unit has a single B* suffix."""
+    """Equal rotations: BWT bytes are canonical, the block is flagged with its multiplicity q, and origPtr is the
+    reference's own choice inside the tie group -- closed form for units with a single B* suffix, the tie-order replay
+    (stage2_tie.cu) for the others.  Every one of the 325 golden origPtr values minted from the reference."""
     eng = engine_for(9)
-    gold = {(g["unit"], g["q"]): g["orig_ptr"] for g in json.load(open(os.path.join(G, "origptr_powers.json")))}
-    cases = [(b"ab", 1000), (b"abc", 5000), (b"abcabd", 2049), (b"x", 70000), (b"cab", 33327), (b"aab", 1027), (b"aab", 1028),
-             (b"aab", 13), (b"1234567", 1001), (b"ba", 9), (b"acb", 1026), (b"qqzzq", 100), (b"abc", 299993), (b"abcdcb", 5000)]
-    exact = 0
-    for unit, q in cases:
+    gold = json.load(open(os.path.join(G, "origptr_powers.json")))
+    for g in gold:
+        unit, q = g["unit"].encode("latin-1"), g["q"]
         d = np.frombuffer(unit * q, np.uint8)
         out = eng.compress(d)
-        assert bz2.decompress(out) == d.tobytes()
         enc, _ = S.orc_rle1_emit(d, 0, d.size)
-        bw, lo, qq = S.orc_bwt(enc)
         n = len(enc)
-        assert np.array_equal(eng.fetch("bwt", np.uint8)[:n], bw)
-        assert int(eng.fetch("power_q", np.uint32)[0]) == (qq if qq > 1 else 0)
         op = int(eng.fetch("origptr", np.uint32)[0])
-        assert lo <= op < lo + qq
-        off = S.orc_power_offset(enc, qq)
-        if off >= 0:
-            assert op == lo + off, (unit, q)
-            if (unit.decode("latin-1"), q) in gold and len(enc) == len(d):
-                assert op == gold[(unit.decode("latin-1"), q)], (unit, q)
-                exact += 1
-    assert exact >= 8
+        if n == d.size:                                   # run-free unit: the block is the golden block itself
+            assert op == g["orig_ptr"], g
+        if n <= 120_000 or unit in (b"abcabd", b"cab"):
+            bw, op_exp, qq = S.orc_bwt(enc)
+            assert np.array_equal(eng.fetch("bwt", np.uint8)[:n], bw), g
+            assert int(eng.fetch("power_q", np.uint32)[0]) == (qq if qq > 1 else 0), g
+            assert op == op_exp, g
+            assert out == S.orc_compress(d, 9), g
+
+
+def test_random_power_streams_golden(engine_for):
+    """240 seeded random (u, q) with |u|*q <= 899,981 at -1 and -9: whole streams equal the reference's (sha256 golden)."""
+    gold = json.load(open(os.path.join(G, "powers_random.json")))
+    assert len(gold) >= 200
+    for g in gold:
+        d = S.random_power_case(g["seed"], g["p"], g["alpha"], g["q"])
+        for level in (1, 9):
+            out = engine_for(level).compress(d)
+            assert hashlib.sha256(out).hexdigest() == g[f"sha_L{level}"], (g, level)
+            if level == 9 and "orig_ptr" in g:
+                assert int(engine_for(9).fetch("origptr", np.uint32)[0]) == g["orig_ptr"], g
+
+
+def test_closed_form_equals_replay(monkeypatch):
+    """Units with a single B* suffix take a closed form on the GPU (k_power_origptr); forcing the replay on the same
+    inputs (BZ2_B200_TIE_FORCE=1) must give the same streams."""
+    cases = [(n, d, lv) for n, d, lv in S.power_stream_cases()]
+    for unit, q in [(b"aab", 13), (b"aab", 1027), (b"aab", 1028), (b"abc", 5000), (b"1234567", 1001), (b"ab", 1000), (b"x", 70000),
+                    (b"acb", 1026), (b"qqzzq", 100), (b"zyx", 2049), (b"abc", 33327)]:
+        cases.append((f"{unit!r}^{q}", np.frombuffer(unit * q, np.uint8), 9))
+    plain = {}
+    for level in (1, 2, 3, 5, 9):
+        eng = B.Engine(level=level)
+        try:
+            for name, d, lv in cases:
+                if lv == level:
+                    plain[name] = eng.compress(S.as_u8(d))
+        finally:
+            eng.close()
+    monkeypatch.setenv("BZ2_B200_TIE_FORCE", "1")
+    for level in (1, 2, 3, 5, 9):
+        eng = B.Engine(level=level)
+        try:
+            for name, d, lv in cases:
+                if lv == level:
+                    assert eng.compress(S.as_u8(d)) == plain[name], name
+        finally:
+            eng.close()
 
 
 def test_periodic_segments_resolve_in_one_step(engine_for):
@@ -225,9 +252,7 @@ def test_chains_from_the_first_doubling_round(monkeypatch):
             unit = rng.integers(0, int(rng.integers(1, 257)), int(rng.integers(2, 3000)), dtype=np.uint8)
             d = np.resize(unit, n) if it % 2 else np.concatenate([np.resize(unit, n), rng.integers(0, 256, 7, dtype=np.uint8), np.resize(unit, n)])
             got = eng.compress(d)
-            enc, _ = S.orc_rle1_emit(d, 0, d.size)
-            if S.orc_bwt(enc)[2] == 1:
-                assert got == S.orc_compress(d, 9), (it, n)
+            assert got == S.orc_compress(d, 9), (it, n)
             assert bz2.decompress(got) == d.tobytes(), (it, n)
     finally:
         eng.close()
