@@ -45,6 +45,7 @@ EXPORTS = [
     "bz2b200_engine_destroy", "bz2b200_engine_set_stream", "bz2b200_compress_host", "bz2b200_compress_device", "bz2b200_stream_begin",
     "bz2b200_stream_feed", "bz2b200_debug_keep", "bz2b200_debug_fetch",
     "bz2b200_scan_create", "bz2b200_scan_rescan", "bz2b200_scan_boundary", "bz2b200_scan_destroy", "bz2b200_concat_bits",
+    "bz2b200_multi_create", "bz2b200_multi_destroy", "bz2b200_multi_engines", "bz2b200_multi_compress",
     # include/bzlib.h
     "BZ2_bzCompressInit", "BZ2_bzCompress", "BZ2_bzCompressEnd", "BZ2_bzBuffToBuffCompress",
     "BZ2_bzWriteOpen", "BZ2_bzWrite", "BZ2_bzWriteClose", "BZ2_bzWriteClose64", "BZ2_bzlibVersion",
@@ -120,6 +121,14 @@ def load():
     lib.BZ2_bzclose.argtypes = [vp]
     lib.BZ2_bzerror.restype = C.c_char_p
     lib.BZ2_bzerror.argtypes = [vp, C.POINTER(C.c_int)]
+    lib.bz2b200_multi_create.restype = C.c_int
+    lib.bz2b200_multi_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int, C.c_int, sz]
+    lib.bz2b200_multi_destroy.restype = None
+    lib.bz2b200_multi_destroy.argtypes = [vp]
+    lib.bz2b200_multi_engines.restype = C.c_int
+    lib.bz2b200_multi_engines.argtypes = [vp]
+    lib.bz2b200_multi_compress.restype = C.c_int
+    lib.bz2b200_multi_compress.argtypes = [vp, vp, C.POINTER(vp), sz, vp, C.POINTER(sz), C.c_uint, C.POINTER(Stats)]
     lib.bz2b200_pool_clear.restype = None
     return lib
 
@@ -184,6 +193,51 @@ class Engine:
         got = C.c_size_t(0)
         _check(self.lib.bz2b200_debug_fetch(self.h, name.encode(), buf.ctypes.data, buf.nbytes, C.byref(got)), f"debug_fetch({name})")
         return buf[: got.value // dt.itemsize].copy()
+
+
+class Multi:
+    """Several engines on one stream (bz2b200_multi_*): devices=[0, 1, 2, 3] shards by block over four GPUs,
+    devices=[0, 0] keeps two windows in flight on one."""
+
+    def __init__(self, devices, level=9, window_bytes=0):
+        self.lib = load()
+        self.h = C.c_void_p()
+        self.level = level
+        self.devices = list(devices)
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        _check(self.lib.bz2b200_multi_create(C.byref(self.h), arr, len(self.devices), level, window_bytes), "multi_create")
+
+    def close(self):
+        if self.h:
+            self.lib.bz2b200_multi_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def out_cap(self, n):
+        return int(n * 1.02) + 24576 * (n // (100000 * self.level - 19) + 2) + 1024
+
+    def compress_ptr(self, src_ptr, n, dst_ptr, cap, flags=0, d_srcs=None):
+        """src_ptr: host pointer (or None with d_srcs = one device pointer per engine); dst_ptr: host pointer."""
+        out_len = C.c_size_t(cap)
+        st = Stats()
+        ds = None
+        if d_srcs is not None:
+            ds = (C.c_void_p * len(d_srcs))(*d_srcs)
+        _check(self.lib.bz2b200_multi_compress(self.h, src_ptr, ds, n, dst_ptr, C.byref(out_len), flags, C.byref(st)), "multi_compress")
+        self.stats = st
+        return out_len.value
+
+    def compress(self, data, flags=0):
+        a = np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray)) else np.ascontiguousarray(data, np.uint8)
+        cap = self.out_cap(a.size)
+        out = np.empty(cap, np.uint8)
+        n = self.compress_ptr(_ptr(a), a.size, out.ctypes.data, cap, flags)
+        return out[:n].tobytes()
 
 
 def compress(data, level=9):

@@ -13,6 +13,7 @@
  */
 #include "../../include/bzlib.h"
 #include "../../include/bz2_b200.h"
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <pthread.h>
@@ -73,13 +74,64 @@ static void engine_release(bz2b200_engine* e, int level)
    if (victim) bz2b200_engine_destroy(victim);
 }
 
+/* ---- several engines on one stream (bz2b200_multi_*): BZ2_B200_DEVICES=0,1,2,3 shards the one-shot call by block
+ * over those GPUs; a GPU listed twice (0,0) keeps two windows in flight on it.  One set of engines is kept per
+ * process and reused while level and device list stay the same. */
+static struct { bz2b200_multi* m; int level; char devs[128]; } mpool;
+
+static int parse_devices(const char* v, int* out, int max)
+{
+   int n = 0;
+   while (v && *v && n < max) {
+      char* end;
+      long d = strtol(v, &end, 10);
+      if (end == v) break;
+      out[n++] = (int)d;
+      if (*end != ',') break;
+      v = end + 1;
+   }
+   return n;
+}
+
+static bz2b200_multi* multi_acquire(int level, int* rc_out)
+{
+   const char* v = getenv("BZ2_B200_DEVICES");
+   int devs[16], n;
+   bz2b200_multi* m = NULL;
+   *rc_out = 0;
+   if (!v || !*v) return NULL;
+   n = parse_devices(v, devs, 16);
+   if (n < 2) return NULL;
+   pthread_mutex_lock(&pool_mu);
+   if (mpool.m && mpool.level == level && !strncmp(mpool.devs, v, sizeof mpool.devs)) { m = mpool.m; mpool.m = NULL; }
+   pthread_mutex_unlock(&pool_mu);
+   if (m) return m;
+   *rc_out = bz2b200_multi_create(&m, devs, n, level, (size_t)env_int("BZ2_B200_WINDOW_MB", 0) << 20);
+   return *rc_out ? NULL : m;
+}
+
+static void multi_release(bz2b200_multi* m, int level)
+{
+   const char* v = getenv("BZ2_B200_DEVICES");
+   bz2b200_multi* victim;
+   pthread_mutex_lock(&pool_mu);
+   victim = mpool.m;
+   mpool.m = m; mpool.level = level;
+   snprintf(mpool.devs, sizeof mpool.devs, "%s", v ? v : "");
+   pthread_mutex_unlock(&pool_mu);
+   if (victim) bz2b200_multi_destroy(victim);
+}
+
 /* Called at process exit or by tests that want the HBM back. */
 void bz2b200_pool_clear(void)
 {
    int i;
+   bz2b200_multi* m;
    pthread_mutex_lock(&pool_mu);
    for (i = 0; i < POOL_MAX; i++) if (pool[i].e) { bz2b200_engine_destroy(pool[i].e); pool[i].e = NULL; }
+   m = mpool.m; mpool.m = NULL;
    pthread_mutex_unlock(&pool_mu);
+   if (m) bz2b200_multi_destroy(m);
 }
 
 static int map_engine_error(int rc)
@@ -258,6 +310,19 @@ int BZ2_bzBuffToBuffCompress(char* dest, unsigned int* destLen, char* source, un
    if (dest == NULL || destLen == NULL || source == NULL || blockSize100k < 1 || blockSize100k > 9 ||
        verbosity < 0 || verbosity > 4 || workFactor < 0 || workFactor > 250)
       return BZ_PARAM_ERROR;
+   {
+      bz2b200_multi* m = multi_acquire(blockSize100k, &rc);
+      if (rc) return map_engine_error(rc) == BZ_MEM_ERROR ? BZ_MEM_ERROR : BZ_CONFIG_ERROR;
+      if (m) {
+         dlen = *destLen;
+         rc = bz2b200_multi_compress(m, source, NULL, sourceLen, dest, &dlen, 0, NULL);
+         multi_release(m, blockSize100k);
+         if (rc == BZ2B200_EOUTFULL) return BZ_OUTBUFF_FULL;
+         if (rc) return map_engine_error(rc);
+         *destLen = (unsigned int)dlen;
+         return BZ_OK;
+      }
+   }
    rc = engine_acquire(&eng, blockSize100k);
    if (rc) return map_engine_error(rc) == BZ_MEM_ERROR ? BZ_MEM_ERROR : BZ_CONFIG_ERROR;
    dlen = *destLen;

@@ -4,8 +4,7 @@
 // handle_compress (bzlib.c:361-396) looping copy_input_until_stop + BZ2_compressBlock
 // one 900 kB block at a time; here a window of up to ~100 blocks is taken through each
 // stage with one set of kernel launches.
-#include "engine.h"
-#include "../../include/bz2_b200.h"
+#include "engine_full.h"
 #include <stdlib.h>
 #include <string.h>
 #include <new>
@@ -23,54 +22,13 @@ int engine_fail(Engine* e, cudaError_t c, const char* file, int line)
    return BZ2B200_ECUDA;
 }
 
-static int set_err(int code, const char* msg)
+void set_err_text(const char* msg) { snprintf(g_err, sizeof g_err, "%s", msg); }
+
+int set_err(int code, const char* msg)
 {
    snprintf(g_err, sizeof g_err, "%s", msg);
    return code;
 }
-
-// ---- stream state kept between windows -----------------------------------------------------
-struct StreamState {
-   u64 bits;            // absolute stream bits produced so far
-   u32 combined_crc;    // compress.c:826-828
-   u32 block_no;
-   bool header_done;
-   bool tail_running;   // last byte arrived in BZ_RUN mode
-   // host-side bit carry for the host/stream paths
-   u8  carry; u32 ncarry;
-   size_t h_fill;       // bytes waiting in h_in
-   bz2b200_stats st;
-};
-
-// Streaming feed (bz2b200_stream_feed): the caller's thread only copies input into a pinned ring; a worker
-// thread owned by the engine cuts windows out of it and runs them, so feeding (fread / memcpy in the client)
-// overlaps the GPU work (the reference's BZ2_bzWrite trickle, bzlib.c:1049-1066).
-struct AsyncFeed {
-   pthread_t th;
-   pthread_mutex_t mu;
-   pthread_cond_t cv_work, cv_space, cv_done;
-   bool inited, th_started;
-   size_t cap;                 // ring capacity in bytes (the ring is h_in)
-   u64 head, tail;             // absolute byte counters: the ring holds stream bytes [head, tail)
-   int pending_end;            // closing request posted by the feeding thread: 1 = flush, 2 = finish
-   bool closing_done, busy, quit, hook_advanced;
-   int err;
-   u8* outq; size_t out_len, out_cap;   // compressed bytes produced by the worker, drained by the feeding thread
-};
-
-struct EngineFull : Engine {
-   StreamState ss;
-   AsyncFeed af;
-   bool debug_keep;
-   u32 last_nb, last_E;
-   cudaEvent_t ev[6];
-   // host path: double-buffered input so the next window's H2D overlaps this window's kernels
-   u8* d_in2;
-   cudaStream_t copy_stream;
-   cudaEvent_t ev_h2d[2];
-   void (*after_s1)(EngineFull*, u32 consumed, void* ctx);
-   void* after_s1_ctx;
-};
 
 template <typename T>
 static cudaError_t dalloc(T** p, size_t count)
@@ -82,7 +40,7 @@ static cudaError_t dalloc(T** p, size_t count)
 
 static void feed_shutdown(EngineFull* e);
 
-static void engine_free(EngineFull* e)
+void engine_free(EngineFull* e)
 {
    if (!e) return;
    feed_shutdown(e);
@@ -114,7 +72,7 @@ static void engine_free(EngineFull* e)
    free(e);
 }
 
-static int engine_new(EngineFull** out, int device, int level, size_t window_bytes)
+int engine_new(EngineFull** out, int device, int level, size_t window_bytes)
 {
    int ndev = 0;
    cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -231,7 +189,7 @@ fail:
    return rc ? rc : BZ2B200_ENOMEM;
 }
 
-static int ensure_staging(EngineFull* e, bool need_hin)
+int ensure_staging(EngineFull* e, bool need_hin)
 {
    if (!e->d_in)  { cudaError_t c = cudaMalloc(reinterpret_cast<void**>(&e->d_in), (size_t)e->win_cap + 64); if (c != cudaSuccess) return engine_fail(e, c, __FILE__, __LINE__); }
    if (!e->d_out) { cudaError_t c = cudaMalloc(reinterpret_cast<void**>(&e->d_out), e->out_cap); if (c != cudaSuccess) return engine_fail(e, c, __FILE__, __LINE__); }
@@ -250,7 +208,7 @@ static int ensure_staging(EngineFull* e, bool need_hin)
    return 0;
 }
 
-static void stream_reset(EngineFull* e)
+void stream_reset(EngineFull* e)
 {
    memset(&e->ss, 0, sizeof e->ss);
    e->launches = 0;
@@ -259,7 +217,7 @@ static void stream_reset(EngineFull* e)
 
 // One window through all stages.  d_in: device input; writes coded blocks into d_out at
 // their absolute bit positions (relative to origin_bit) and advances ss.bits.
-static int run_window(EngineFull* e, const u8* d_in, u32 W, bool is_final, bool tail_merge,
+int run_window(EngineFull* e, const u8* d_in, u32 W, bool is_final, bool tail_merge,
                       u8* d_out, u64 origin_bit, u32* consumed, u32* nb_out)
 {
    cudaStream_t st = e->stream;
@@ -546,13 +504,6 @@ static int feed_drain(EngineFull* e, bz2b200_sink sink, void* user)
    free(buf);
    return rc;
 }
-
-// Makes the engine's device current for the duration of a C-ABI call and restores the caller's.
-struct DeviceGuard {
-   int prev;
-   explicit DeviceGuard(int dev) : prev(-1) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
-   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
-};
 
 } // namespace bz
 

@@ -1,0 +1,361 @@
+// multi.cu -- one .bz2 stream compressed by several engines at once (bz2b200_multi_* in include/bz2_b200.h).
+//
+// The reference handles one block at a time (handle_compress, bzlib.c:361-396); one engine here handles one
+// window (~100 blocks) at a time.  Windows of a stream are independent except for two scalars:
+//   chain A  where the window starts: the previous window ends at its last complete block, which stage 1
+//            (RLE1 split) of THAT window decides (bzlib.c:227, :383).  One integer, known ~1 ms into the window.
+//   chain B  the bit position of the window's output in the stream and the combined CRC so far
+//            (compress.c:37-86 bsBuff/bsLive persist across blocks; compress.c:826-828).  Two integers, known
+//            when the previous window has been coded.
+// So consecutive windows go round-robin to E engines, each on its own thread and CUDA stream.  The engines may sit
+// on E different GPUs (sharded by block, host-side gather, no collective) or several on ONE GPU, where
+// the latency-bound stages of one window (S1, S3, S4) run under the sort of the next.  Every engine copies its own
+// windows host->device (prefetched: the copy of window w+E starts as soon as stage 1 of window w has run) and
+// writes its own output straight into the caller's buffer at the final byte offset; output that does not start on
+// a byte boundary is shifted on the device first (k_concat_bits) and the two bytes at each seam are OR-ed on the
+// host.  No torch, no NCCL: host integers and cudaMemcpyAsync only.
+#include "engine_full.h"
+#include <stdlib.h>
+#include <string.h>
+
+namespace bz {
+
+int concat_bits_stream(u8* d_dst, u64 dst_bit, const u8* d_src, u64 nbits, cudaStream_t st);
+
+constexpr int MAX_ENGINES = 16;
+constexpr size_t PF_SLACK1 = (size_t)2 << 20;        // how far short of a full window a window may stop (run-free data: < 0.9 MB)
+
+struct Multi;
+
+struct Seam { u64 bit0, bit1; u8 head, tail; };      // window output = stream bits [bit0, bit1); partial first / last byte
+
+struct MWorker {
+   Multi* m; int idx;
+   EngineFull* e;
+   pthread_t th; bool started;
+   u64 seen_seq;
+   u8* dbuf[2]; size_t dcap; int cur;               // device input staging (host sources)
+   size_t pf_lo, pf_len; bool pf_valid;
+   cudaStream_t copy_stream; cudaEvent_t ev_pf;
+   u8* d_shift; u8* h_seam;                          // shifted output; pinned scratch for the seam bytes
+};
+
+struct MJob {
+   const u8* src; const u8* const* dsrc; size_t n;
+   u8* dst; size_t cap; unsigned flags; bool pinned;
+   pthread_mutex_t mu; pthread_cond_t cv;
+   u64 a_w; size_t a_start; bool a_done;            // chain A: window a_w starts at a_start
+   u64 b_w; u64 b_bits; u32 b_crc;                   // chain B: window b_w's output starts at bit b_bits
+   Seam* seams; size_t n_seams, cap_seams;
+   int err; char errtext[256];
+};
+
+struct Multi {
+   int n; int level;
+   MWorker w[MAX_ENGINES];
+   MJob job;
+   pthread_mutex_t mu; pthread_cond_t cv_job, cv_done;
+   u64 job_seq; int n_done; bool quit;
+   pthread_mutex_t call_mu;                          // one job at a time
+};
+
+static void job_fail(MJob& J, int rc, const char* text)
+{
+   pthread_mutex_lock(&J.mu);
+   if (!J.err) { J.err = rc; snprintf(J.errtext, sizeof J.errtext, "%s", text ? text : ""); }
+   pthread_cond_broadcast(&J.cv);
+   pthread_mutex_unlock(&J.mu);
+}
+
+struct HookCtx { MWorker* wk; u64 w; size_t start, W; bool fin; };
+
+// stage 1 of window w has run: hand the start of window w+1 to whoever waits for it, then start copying the input of
+// this engine's next window (w+E) -- its start is not known yet, so copy a region that covers every start it can have
+static void multi_after_s1(EngineFull* e, u32 cons, void* vctx)
+{
+   HookCtx* c = static_cast<HookCtx*>(vctx);
+   MWorker* wk = c->wk; Multi* m = wk->m; MJob& J = m->job;
+   pthread_mutex_lock(&J.mu);
+   J.a_w = c->w + 1;
+   J.a_start = c->start + cons;
+   if (c->fin || cons == 0) J.a_done = true;
+   pthread_cond_broadcast(&J.cv);
+   pthread_mutex_unlock(&J.mu);
+   if (J.dsrc || !J.pinned || c->fin || cons == 0) return;
+   const size_t E = (size_t)m->n;
+   const size_t next1 = c->start + cons;                                   // start of window w+1
+   const size_t back = (E - 1) * PF_SLACK1;
+   size_t lo = next1 + (E - 1) * (size_t)e->win_cap;
+   lo = (lo > back + next1) ? lo - back : next1;
+   if (lo >= J.n) return;
+   size_t len = (size_t)e->win_cap + back;
+   if (len > J.n - lo) len = J.n - lo;
+   if (len > wk->dcap) len = wk->dcap;
+   const int nb = wk->cur ^ 1;
+   if (cudaMemcpyAsync(wk->dbuf[nb], J.src + lo, len, cudaMemcpyHostToDevice, wk->copy_stream) != cudaSuccess) { cudaGetLastError(); return; }
+   cudaEventRecord(wk->ev_pf, wk->copy_stream);
+   wk->pf_lo = lo; wk->pf_len = len; wk->pf_valid = true;
+}
+
+static int run_job(MWorker* wk)
+{
+   Multi* m = wk->m; MJob& J = m->job; EngineFull* e = wk->e;
+   const u64 E = (u64)m->n;
+   const bool tail_merge = !(J.flags & BZ2B200_TAIL_STREAMED);
+   cudaStream_t st = e->stream;
+   stream_reset(e);
+   e->ss.header_done = true;
+   wk->pf_valid = false;
+   for (u64 w = (u64)wk->idx; ; w += E) {
+      pthread_mutex_lock(&J.mu);
+      while (!J.err && !J.a_done && J.a_w < w) pthread_cond_wait(&J.cv, &J.mu);
+      if (J.err || J.a_w < w) { pthread_mutex_unlock(&J.mu); break; }     // failed, or the input ended before this window
+      const size_t start = J.a_start;
+      pthread_mutex_unlock(&J.mu);
+      if (start >= J.n) break;
+      const size_t W = (J.n - start < e->win_cap) ? (J.n - start) : e->win_cap;
+      const bool fin = (start + W == J.n);
+      const u8* d_in;
+      if (J.dsrc) d_in = J.dsrc[wk->idx] + start;
+      else if (wk->pf_valid && start >= wk->pf_lo && start + W <= wk->pf_lo + wk->pf_len) {
+         wk->cur ^= 1;
+         BZ_CUDA(e, cudaStreamWaitEvent(st, wk->ev_pf, 0));
+         d_in = wk->dbuf[wk->cur] + (start - wk->pf_lo);
+      } else {
+         if (wk->pf_valid) BZ_CUDA(e, cudaStreamSynchronize(wk->copy_stream));                      // a guess that missed
+         BZ_CUDA(e, cudaMemcpyAsync(wk->dbuf[wk->cur], J.src + start, W, cudaMemcpyHostToDevice, st));
+         d_in = wk->dbuf[wk->cur];
+      }
+      wk->pf_valid = false;
+      HookCtx ctx = { wk, w, start, W, fin };
+      e->after_s1 = multi_after_s1; e->after_s1_ctx = &ctx;
+      BZ_CUDA(e, cudaMemsetAsync(e->d_out, 0, e->out_cap, st));
+      e->ss.bits = 0; e->ss.combined_crc = 0;
+      const u32 blocks_before = e->ss.block_no;
+      u32 cons = 0, nb = 0;
+      const int rc = run_window(e, d_in, (u32)W, fin, tail_merge, e->d_out, 0, &cons, &nb);
+      e->after_s1 = nullptr;
+      if (rc) return rc;
+      if (cons == 0 || nb == 0) return set_err(BZ2B200_EINTERNAL, "window made no progress");
+      (void)blocks_before;
+      const u64 bits_w = e->ss.bits;
+      const u32 fold_w = e->ss.combined_crc;
+      // chain B: my output starts where the previous window's ended
+      pthread_mutex_lock(&J.mu);
+      while (!J.err && J.b_w < w) pthread_cond_wait(&J.cv, &J.mu);
+      if (J.err) { pthread_mutex_unlock(&J.mu); break; }
+      const u64 B = J.b_bits;
+      const u32 r32 = nb & 31u;
+      J.b_crc = (r32 ? ((J.b_crc << r32) | (J.b_crc >> (32 - r32))) : J.b_crc) ^ fold_w;
+      J.b_bits = B + bits_w;
+      J.b_w = w + 1;
+      if (w >= J.cap_seams) {
+         size_t nc = J.cap_seams ? J.cap_seams * 2 : 64;
+         while (nc <= w) nc *= 2;
+         Seam* ns = static_cast<Seam*>(realloc(J.seams, nc * sizeof(Seam)));
+         if (!ns) { pthread_mutex_unlock(&J.mu); return set_err(BZ2B200_ENOMEM, "out of host memory"); }
+         J.seams = ns; J.cap_seams = nc;
+      }
+      if (w + 1 > J.n_seams) J.n_seams = w + 1;
+      pthread_cond_broadcast(&J.cv);
+      pthread_mutex_unlock(&J.mu);
+      // output: whole bytes go straight to their final place, the partial bytes at both ends are kept for the seams
+      const u32 r = (u32)(B & 7);
+      const u64 endrel = r + bits_w;                                     // bits used in the (shifted) buffer
+      if (((B + bits_w + 7) >> 3) + 12 > J.cap) return set_err(BZ2B200_EOUTFULL, "destination too small");
+      const u8* srcbuf = e->d_out;
+      if (r) {
+         BZ_CUDA(e, cudaMemsetAsync(wk->d_shift, 0, (size_t)((endrel + 7) >> 3) + 8, st));
+         if (concat_bits_stream(wk->d_shift, r, e->d_out, bits_w, st)) return set_err(BZ2B200_ECUDA, "bit shift failed");
+         e->launches++;
+         srcbuf = wk->d_shift;
+      }
+      const size_t i0 = r ? 1 : 0, i1 = (size_t)(endrel >> 3);
+      if (i1 > i0) BZ_CUDA(e, cudaMemcpyAsync(J.dst + (B >> 3) + i0, srcbuf + i0, i1 - i0, cudaMemcpyDeviceToHost, st));
+      BZ_CUDA(e, cudaMemcpyAsync(wk->h_seam, srcbuf, 1, cudaMemcpyDeviceToHost, st));
+      BZ_CUDA(e, cudaMemcpyAsync(wk->h_seam + 8, srcbuf + i1, 1, cudaMemcpyDeviceToHost, st));
+      BZ_CUDA(e, cudaStreamSynchronize(st));
+      pthread_mutex_lock(&J.mu);
+      Seam& s = J.seams[w];
+      s.bit0 = B; s.bit1 = B + bits_w;
+      s.head = r ? wk->h_seam[0] : 0;
+      s.tail = (endrel & 7) ? wk->h_seam[8] : 0;
+      pthread_mutex_unlock(&J.mu);
+      if (fin) break;
+   }
+   return 0;
+}
+
+static void* worker_main(void* arg)
+{
+   MWorker* wk = static_cast<MWorker*>(arg);
+   Multi* m = wk->m;
+   cudaSetDevice(wk->e->device);
+   pthread_mutex_lock(&m->mu);
+   for (;;) {
+      while (!m->quit && m->job_seq == wk->seen_seq) pthread_cond_wait(&m->cv_job, &m->mu);
+      if (m->quit) break;
+      wk->seen_seq = m->job_seq;
+      pthread_mutex_unlock(&m->mu);
+      const int rc = run_job(wk);
+      if (rc) job_fail(m->job, rc, wk->e->err[0] ? wk->e->err : bz2b200_last_error());
+      cudaStreamSynchronize(wk->copy_stream);
+      pthread_mutex_lock(&m->mu);
+      m->n_done++;
+      pthread_cond_broadcast(&m->cv_done);
+   }
+   pthread_mutex_unlock(&m->mu);
+   return nullptr;
+}
+
+static void multi_free(Multi* m)
+{
+   if (!m) return;
+   pthread_mutex_lock(&m->mu);
+   m->quit = true;
+   pthread_cond_broadcast(&m->cv_job);
+   pthread_mutex_unlock(&m->mu);
+   for (int k = 0; k < m->n; k++) {
+      MWorker& w = m->w[k];
+      if (w.started) pthread_join(w.th, nullptr);
+      if (w.e) {
+         cudaSetDevice(w.e->device);
+         for (int i = 0; i < 2; i++) if (w.dbuf[i]) cudaFree(w.dbuf[i]);
+         if (w.d_shift) cudaFree(w.d_shift);
+         if (w.h_seam) cudaFreeHost(w.h_seam);
+         if (w.copy_stream) cudaStreamDestroy(w.copy_stream);
+         if (w.ev_pf) cudaEventDestroy(w.ev_pf);
+         engine_free(w.e);
+      }
+   }
+   free(m->job.seams);
+   pthread_mutex_destroy(&m->job.mu); pthread_cond_destroy(&m->job.cv);
+   pthread_mutex_destroy(&m->mu); pthread_cond_destroy(&m->cv_job); pthread_cond_destroy(&m->cv_done);
+   pthread_mutex_destroy(&m->call_mu);
+   free(m);
+}
+
+} // namespace bz
+
+using namespace bz;
+
+extern "C" {
+
+struct bz2b200_multi;
+
+int bz2b200_multi_create(bz2b200_multi** out, const int* devices, int n_engines, int block_size_100k, size_t window_bytes)
+{
+   if (!out || !devices || n_engines < 1 || n_engines > MAX_ENGINES) return set_err(BZ2B200_EPARAM, "bad argument");
+   int prev = -1;
+   cudaGetDevice(&prev);
+   Multi* m = static_cast<Multi*>(calloc(1, sizeof(Multi)));
+   if (!m) return set_err(BZ2B200_ENOMEM, "out of host memory");
+   m->n = n_engines; m->level = block_size_100k;
+   pthread_mutex_init(&m->mu, nullptr); pthread_cond_init(&m->cv_job, nullptr); pthread_cond_init(&m->cv_done, nullptr);
+   pthread_mutex_init(&m->job.mu, nullptr); pthread_cond_init(&m->job.cv, nullptr);
+   pthread_mutex_init(&m->call_mu, nullptr);
+   int rc = 0;
+   for (int k = 0; k < n_engines && !rc; k++) {
+      MWorker& w = m->w[k];
+      w.m = m; w.idx = k;
+      rc = engine_new(&w.e, devices[k], block_size_100k, window_bytes);
+      if (rc) break;
+      EngineFull* e = w.e;
+      w.dcap = (size_t)e->win_cap + (size_t)(n_engines - 1) * PF_SLACK1;
+      bool ok = true;
+      for (int i = 0; i < 2; i++) ok = ok && cudaMalloc(reinterpret_cast<void**>(&w.dbuf[i]), w.dcap + 64) == cudaSuccess;
+      ok = ok && cudaMalloc(reinterpret_cast<void**>(&w.d_shift), e->out_cap + 64) == cudaSuccess;
+      ok = ok && cudaMalloc(reinterpret_cast<void**>(&e->d_out), e->out_cap) == cudaSuccess;
+      ok = ok && cudaMallocHost(reinterpret_cast<void**>(&w.h_seam), 64) == cudaSuccess;
+      ok = ok && cudaStreamCreateWithFlags(&w.copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+      ok = ok && cudaEventCreateWithFlags(&w.ev_pf, cudaEventDisableTiming) == cudaSuccess;
+      if (!ok) { cudaGetLastError(); rc = set_err(BZ2B200_ENOMEM, "device allocation failed (multi-engine staging)"); break; }
+      if (pthread_create(&w.th, nullptr, worker_main, &w) != 0) { rc = set_err(BZ2B200_ENOMEM, "cannot start an engine thread"); break; }
+      w.started = true;
+   }
+   if (prev >= 0) cudaSetDevice(prev);
+   if (rc) { multi_free(m); return rc; }
+   *out = reinterpret_cast<bz2b200_multi*>(m);
+   return 0;
+}
+
+void bz2b200_multi_destroy(bz2b200_multi* h)
+{
+   int prev = -1;
+   cudaGetDevice(&prev);
+   multi_free(reinterpret_cast<Multi*>(h));
+   if (prev >= 0) cudaSetDevice(prev);
+}
+
+int bz2b200_multi_engines(const bz2b200_multi* h) { return h ? reinterpret_cast<const Multi*>(h)->n : 0; }
+
+static void put_bits_host(u8* dst, u64* bit, u64 value, int nbits)
+{
+   for (int k = nbits - 1; k >= 0; k--) {
+      if ((value >> k) & 1) dst[*bit >> 3] |= (u8)(0x80u >> (*bit & 7));
+      (*bit)++;
+   }
+}
+
+// src: host pointer to the whole input, or NULL when d_srcs is given: d_srcs[k] is a device pointer, on engine k's
+// GPU, to a resident copy of the whole input (engines on one GPU may share one copy).  dst: host memory.
+int bz2b200_multi_compress(bz2b200_multi* h, const void* src, const void* const* d_srcs, size_t n,
+                           void* dst, size_t* dst_len, unsigned flags, bz2b200_stats* stats)
+{
+   Multi* m = reinterpret_cast<Multi*>(h);
+   if (!m || !dst || !dst_len || (!src && !d_srcs && n)) return set_err(BZ2B200_EPARAM, "bad argument");
+   if (*dst_len < 14) return set_err(BZ2B200_EOUTFULL, "destination too small");
+   pthread_mutex_lock(&m->call_mu);
+   MJob& J = m->job;
+   J.src = static_cast<const u8*>(src); J.dsrc = reinterpret_cast<const u8* const*>(d_srcs); J.n = n;
+   J.dst = static_cast<u8*>(dst); J.cap = *dst_len; J.flags = flags;
+   J.pinned = false;
+   if (src && n) {
+      cudaPointerAttributes at;
+      if (cudaPointerGetAttributes(&at, src) == cudaSuccess) J.pinned = (at.type == cudaMemoryTypeHost);
+      else cudaGetLastError();
+   }
+   J.a_w = 0; J.a_start = 0; J.a_done = (n == 0);
+   J.b_w = 0; J.b_bits = 32; J.b_crc = 0;
+   J.n_seams = 0; J.err = 0; J.errtext[0] = 0;
+   pthread_mutex_lock(&m->mu);
+   m->n_done = 0;
+   m->job_seq++;
+   pthread_cond_broadcast(&m->cv_job);
+   while (m->n_done < m->n) pthread_cond_wait(&m->cv_done, &m->mu);
+   pthread_mutex_unlock(&m->mu);
+   int rc = J.err;
+   if (rc) { set_err_text(J.errtext); pthread_mutex_unlock(&m->call_mu); return rc; }
+   // stream header, the seam bytes, trailer (compress.c:841-845, :872-880)
+   u8* out = J.dst;
+   const u32 magic = 0x425A6830u + (u32)m->level;
+   out[0] = (u8)(magic >> 24); out[1] = (u8)(magic >> 16); out[2] = (u8)(magic >> 8); out[3] = (u8)magic;
+   for (size_t w = 0; w < J.n_seams; w++) {
+      const Seam& s = J.seams[w];
+      if (s.bit0 & 7) out[s.bit0 >> 3] = (u8)(J.seams[w - 1].tail | s.head);
+   }
+   u64 bit = J.b_bits;
+   if (((bit + 80 + 7) >> 3) > J.cap) { pthread_mutex_unlock(&m->call_mu); return set_err(BZ2B200_EOUTFULL, "destination too small"); }
+   out[bit >> 3] = (bit & 7) ? J.seams[J.n_seams - 1].tail : 0;
+   for (u64 k = (bit >> 3) + 1; k <= ((bit + 80) >> 3); k++) out[k] = 0;
+   put_bits_host(out, &bit, 0x177245385090ULL, 48);
+   put_bits_host(out, &bit, J.b_crc, 32);
+   *dst_len = (size_t)((bit + 7) >> 3);
+   if (stats) {
+      bz2b200_stats t;
+      memset(&t, 0, sizeof t);
+      for (int k = 0; k < m->n; k++) {
+         const bz2b200_stats& s = m->w[k].e->ss.st;
+         t.n_blocks += s.n_blocks; t.n_windows += s.n_windows; t.sum_nblock += s.sum_nblock; t.sum_nmtf += s.sum_nmtf;
+         t.n_power_blocks += s.n_power_blocks;
+         t.ms_total += s.ms_total; t.ms_s1 += s.ms_s1; t.ms_s2 += s.ms_s2; t.ms_s3 += s.ms_s3; t.ms_s4 += s.ms_s4;
+         t.bwt_rounds += s.bwt_rounds; t.kernel_launches += s.kernel_launches;
+      }
+      t.in_bytes = n; t.out_bytes = *dst_len; t.combined_crc = J.b_crc; t.out_bits = bit;
+      *stats = t;
+   }
+   pthread_mutex_unlock(&m->call_mu);
+   return 0;
+}
+
+} // extern "C"

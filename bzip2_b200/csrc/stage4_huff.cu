@@ -536,6 +536,15 @@ int concat_bits_device(u8* d_dst, u64 dst_bit, const u8* d_src, u64 nbits)
    return cudaDeviceSynchronize() == cudaSuccess ? 0 : -1;
 }
 
+// the same on a given stream, without synchronising (multi.cu: a window's output shifted to its bit position in the stream)
+int concat_bits_stream(u8* d_dst, u64 dst_bit, const u8* d_src, u64 nbits, cudaStream_t st)
+{
+   if (nbits == 0) return 0;
+   const u64 nwords = (nbits + 31) >> 5;
+   k_concat_bits<<<(unsigned)((nwords + 255) / 256), 256, 0, st>>>(reinterpret_cast<u32*>(d_dst), dst_bit, reinterpret_cast<const u32*>(d_src), nbits);
+   return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
 int put_bits_device(Engine* e, u8* d_out, u64 origin_bit, u64 bitpos, u64 value, int nbits)
 {
    k_put_bits<<<1, 1, 0, e->stream>>>(reinterpret_cast<u32*>(d_out), bitpos - origin_bit, value, nbits);

@@ -69,7 +69,7 @@ int  bz2b200_device_count(void);
 const char* bz2b200_last_error(void);
 const char* bz2b200_version(void);
 
-/* window_bytes = 0 picks the default (128 MiB of input per window). */
+/* window_bytes = 0 picks the default (96 MiB of input per window; at most 100 MiB, at least one block of pure runs). */
 int  bz2b200_engine_create(bz2b200_engine** out, int device, int block_size_100k, size_t window_bytes);
 void bz2b200_engine_destroy(bz2b200_engine* e);
 /* Run on the caller's CUDA stream (a cudaStream_t); NULL restores the engine's own stream. */
@@ -112,6 +112,25 @@ int  bz2b200_scan_boundary(bz2b200_scan* s, size_t start, size_t limit, unsigned
                            size_t* boundary, uint32_t* n_blocks);
 void bz2b200_scan_destroy(bz2b200_scan* s);
 int  bz2b200_concat_bits(int device, void* d_dst, uint64_t dst_bit, const void* d_src, uint64_t nbits);
+
+/* ---- several engines on one stream (multi.cu) ---------------------------------------------------
+ * Consecutive windows (~100 blocks each) of ONE stream go round-robin to n_engines engines, each on
+ * its own thread and CUDA stream; devices[k] is the GPU of engine k.  Different GPUs: the stream is
+ * sharded by block over them with a host-side gather (replaces nothing in the reference,
+ * which is single-threaded -- the unit of work is still BZ2_compressBlock, compress.c:822-881).  The
+ * same GPU listed twice: two windows in flight on it.  Windows are chained by two host integers (where
+ * the next window starts, bzlib.c:227/:383; at which bit its output starts, compress.c:37-86), every
+ * engine copies its own input and writes its own output into the caller's buffer; no collective.
+ * The result is byte-identical to bz2b200_compress_host on one engine.
+ *   multi_compress   src: host pointer to the whole input -- or NULL with d_srcs[k] = device pointer,
+ *                    on engine k's GPU, to a resident copy of the whole input.  dst: host memory,
+ *                    *dst_len capacity in / bytes out.  flags: BZ2B200_TAIL_STREAMED.            */
+typedef struct bz2b200_multi bz2b200_multi;
+int  bz2b200_multi_create(bz2b200_multi** out, const int* devices, int n_engines, int block_size_100k, size_t window_bytes);
+void bz2b200_multi_destroy(bz2b200_multi* m);
+int  bz2b200_multi_engines(const bz2b200_multi* m);
+int  bz2b200_multi_compress(bz2b200_multi* m, const void* src, const void* const* d_srcs, size_t n,
+                            void* dst, size_t* dst_len, unsigned flags, bz2b200_stats* stats);
 
 /* Per-stage intermediates of the LAST window processed (tests only).
  * name: "X" "P" "crc" "origptr" "power_q" "inuse" "ninuse" "nmtf" "mtffreq" "bits" "bitoff"
