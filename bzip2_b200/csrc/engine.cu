@@ -135,6 +135,7 @@ int engine_new(EngineFull** out, int device, int level, size_t window_bytes)
       }
       if (stage2_init() != 0) { rc = engine_fail(e, cudaGetLastError(), __FILE__, __LINE__); goto fail; }
       c0 = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
+      if (c0 == cudaSuccess) c0 = cudaEventCreateWithFlags(&e->ev_s1, cudaEventDisableTiming);
       if (c0 != cudaSuccess) { rc = engine_fail(e, c0, __FILE__, __LINE__); goto fail; }
       ALLOC(e->enc, E + 64); ALLOC(e->cend, E + 64);
       ALLOC(e->sa, E + 64); ALLOC(e->rank, E + 64);

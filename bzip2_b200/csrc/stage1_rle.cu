@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(S1_THREADS) k_tile(S1Params p)
    if (MODE == S1_FIND) {
       // one CTA per boundary: locate the tile whose encoded range contains X[b]
       const u32 b = blockIdx.x + 1;
+      if (p.nb_find && blockIdx.x >= p.scalars[0]) return;      // grid sized by an upper bound; scalars[0] = blocks found
       findX = p.X[b];
       const u32 ntiles = (p.W + align + S1_TILE - 1) / S1_TILE;
       if (findX >= p.scalars[2]) { if (threadIdx.x == 0) p.P[b] = p.W; return; }
@@ -373,8 +374,9 @@ __device__ __forceinline__ u32 gf_xpow8(const u32* pw, u64 m)
 constexpr int CRC_THREADS = 256;
 constexpr int CRC_CTAS_PER_BLOCK = 16;
 
-__global__ void __launch_bounds__(CRC_THREADS) k_crc(const u8* in, const u32* P, u32* crc_acc)
+__global__ void __launch_bounds__(CRC_THREADS) k_crc(const u8* in, const u32* P, u32* crc_acc, const u32* nb_dev)
 {
+   if (blockIdx.y >= *nb_dev) return;                // grid sized by an upper bound of the block count
    __shared__ u32 tab[4][256];       // slicing-by-4: tab[k][b] = crc0 of byte b followed by k zero bytes
    __shared__ u32 pw[40];
    __shared__ u32 red[CRC_THREADS];
@@ -439,10 +441,18 @@ __global__ void __launch_bounds__(CRC_THREADS) k_crc(const u8* in, const u32* P,
    }
 }
 
-__global__ void k_crc_final(u32* crc, u32 nb)
+__global__ void k_crc_final(u32* crc, const u32* scalars)
 {
+   const u32 nb = scalars[0];
    u32 b = blockIdx.x * blockDim.x + threadIdx.x;
    if (b < nb) crc[b] = ~crc[b];
+}
+
+// input bytes consumed by the window's complete blocks, next to the other scalars the host reads
+__global__ void k_s1_consumed(const u32* P, u32* scalars)
+{
+   const u32 nb = scalars[0];
+   scalars[3] = nb ? P[nb] : 0;
 }
 
 int stage1_run(Engine* e, const u8* d_in, u32 W, bool is_final, bool tail_merge,
@@ -458,30 +468,33 @@ int stage1_run(Engine* e, const u8* d_in, u32 W, bool is_final, bool tail_merge,
    p.enc = e->enc; p.cend = e->cend; p.X = e->bt.X; p.P = e->bt.P; p.nb_find = 0; p.scalars = e->s1_scalars;
    p.prev_byte = 256; p.carry0 = 0; p.Q = nullptr; p.EQ = nullptr;
 
+   // One host round trip per window: everything below is sized by upper bounds (RLE1 grows the data by at most 5/4,
+   // a block holds at least nmax encoded bytes) and reads the actual counts from device memory.
+   const u32 Eub = W + W / 4 + 64;
+   u32 nb_ub = Eub / e->nmax + 2;
+   if (nb_ub > e->blk_cap) nb_ub = e->blk_cap;
+   if (Eub > e->enc_cap) { snprintf(e->err, sizeof e->err, "window %u too large for the engine (capacity %u)", W, e->win_cap); return -3; }
+   p.nb_find = 1;
    k_tile<S1_AGG><<<ntiles, S1_THREADS, 0, st>>>(p);                                   BZ_KCHECK(e);
    k_scan_runs<<<1, 1024, 0, st>>>(e->tile_len, e->tile_ext, e->tile_carry, ntiles, 0);   BZ_KCHECK(e);
    k_tile<S1_COUNT><<<ntiles, S1_THREADS, 0, st>>>(p);                                 BZ_KCHECK(e);
    k_scan_u32<<<1, 1024, 0, st>>>(e->tile_size, e->tile_base, ntiles, e->s1_scalars + 2); BZ_KCHECK(e);
-   BZ_CUDA(e, cudaMemcpyAsync(e->h_scalars, e->s1_scalars, 4 * sizeof(u32), cudaMemcpyDeviceToHost, st));
-   BZ_CUDA(e, cudaStreamSynchronize(st));
-   const u32 Etot = e->h_scalars[2];
-   if (Etot > e->enc_cap) { snprintf(e->err, sizeof e->err, "encoded window %u exceeds capacity %u", Etot, e->enc_cap); return -3; }
-   BZ_CUDA(e, cudaMemsetAsync(e->cend, 0, (size_t)Etot + 16, st));
+   BZ_CUDA(e, cudaMemsetAsync(e->cend, 0, (size_t)Eub + 16, st));
    k_tile<S1_SCATTER><<<ntiles, S1_THREADS, 0, st>>>(p);                               BZ_KCHECK(e);
    k_chain<<<1, 32, 0, st>>>(e->cend, e->bt.X, e->s1_scalars, e->nmax, is_final ? 1 : 0, tail_merge ? 1 : 0, e->blk_cap); BZ_KCHECK(e);
+   BZ_CUDA(e, cudaMemsetAsync(e->bt.P, 0, sizeof(u32), st));
+   k_tile<S1_FIND><<<nb_ub, S1_THREADS, 0, st>>>(p);                                   BZ_KCHECK(e);
+   k_s1_consumed<<<1, 1, 0, st>>>(e->bt.P, e->s1_scalars);                             BZ_KCHECK(e);
    BZ_CUDA(e, cudaMemcpyAsync(e->h_scalars, e->s1_scalars, 4 * sizeof(u32), cudaMemcpyDeviceToHost, st));
-   BZ_CUDA(e, cudaStreamSynchronize(st));
+   BZ_CUDA(e, cudaEventRecord(e->ev_s1, st));
+   // the block CRCs are not needed to place the next window: they run behind the round trip
+   BZ_CUDA(e, cudaMemsetAsync(e->bt.crc, 0, sizeof(u32) * nb_ub, st));
+   k_crc<<<dim3(CRC_CTAS_PER_BLOCK, nb_ub), CRC_THREADS, 0, st>>>(d_in, e->bt.P, e->bt.crc, e->s1_scalars); BZ_KCHECK(e);
+   k_crc_final<<<(nb_ub + 255) / 256, 256, 0, st>>>(e->bt.crc, e->s1_scalars);            BZ_KCHECK(e);
+   BZ_CUDA(e, cudaEventSynchronize(e->ev_s1));
    const u32 nb = e->h_scalars[0];
    *nb_out = nb; *enc_total_out = e->h_scalars[1];
-   if (nb == 0) { *consumed_out = 0; return 0; }
-   BZ_CUDA(e, cudaMemsetAsync(e->bt.P, 0, sizeof(u32), st));
-   k_tile<S1_FIND><<<nb, S1_THREADS, 0, st>>>(p);                                      BZ_KCHECK(e);
-   BZ_CUDA(e, cudaMemsetAsync(e->bt.crc, 0, sizeof(u32) * nb, st));
-   k_crc<<<dim3(CRC_CTAS_PER_BLOCK, nb), CRC_THREADS, 0, st>>>(d_in, e->bt.P, e->bt.crc); BZ_KCHECK(e);
-   k_crc_final<<<(nb + 255) / 256, 256, 0, st>>>(e->bt.crc, nb);                        BZ_KCHECK(e);
-   BZ_CUDA(e, cudaMemcpyAsync(e->h_scalars + 8, e->bt.P + nb, sizeof(u32), cudaMemcpyDeviceToHost, st));
-   BZ_CUDA(e, cudaStreamSynchronize(st));
-   *consumed_out = e->h_scalars[8];
+   *consumed_out = nb ? e->h_scalars[3] : 0;
    return 0;
 }
 

@@ -15,6 +15,7 @@ import support as S
 import bzip2_b200 as B
 from bzip2_b200 import binding
 from golden.make_golden import stream_cases
+from sharding_oracle import OracleBackend
 
 pytestmark = pytest.mark.gpu
 G = S.GOLDEN
@@ -420,7 +421,7 @@ def test_large_text_roundtrip_and_accounting(engine_for):
 def test_scan_boundary_matches_oracle():
     from bzip2_b200 import sharding as sh
     be = sh.GpuBackend(1, 0)
-    ob = sh.OracleBackend(1)
+    ob = OracleBackend(1)
     data = np.concatenate([S.gen_text(300_000), np.full(200_000, 9, np.uint8), S.gen_random(150_000), S.gen_runs(900_000, seed=8)])
     reg = be.load(data)
     scan = be.scan(reg, 256, 0, True)

@@ -11,6 +11,7 @@ import pytest
 
 import support as S
 from bzip2_b200 import sharding as sh
+from sharding_oracle import OracleBackend
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -36,7 +37,7 @@ def test_sharded_equals_single_stream(name, world, level):
     }[name]()
     shards = _split(data, world)
     halos = sh.make_halos(shards, 6_000_000)
-    out, infos = sh.run_threads(world, lambda r: sh.OracleBackend(level), shards, halos, level)
+    out, infos = sh.run_threads(world, lambda r: OracleBackend(level), shards, halos, level)
     assert out == S.orc_compress(data, level)
     segs = [i["segment"] for i in infos if i["segment"][1] > i["segment"][0]]     # non-empty segments tile the input
     assert segs[0][0] == 0 and segs[-1][1] == data.size
@@ -49,7 +50,7 @@ def test_run_state_across_shards():
     data = np.concatenate([S.gen_text(100_000), np.full(300_000, 7, np.uint8), S.gen_text(250_000, seed=3)])
     for cut in (100_010, 100_255, 100_256, 250_000, 399_999):
         shards = _split(data, 2, [cut])
-        out, _ = sh.run_threads(2, lambda r: sh.OracleBackend(1), shards, sh.make_halos(shards, 2_000_000), 1)
+        out, _ = sh.run_threads(2, lambda r: OracleBackend(1), shards, sh.make_halos(shards, 2_000_000), 1)
         assert out == S.orc_compress(data, 1), cut
 
 
@@ -78,7 +79,7 @@ def _gloo_worker(rank, world, port, path):
     data = S2.gen_mixed(800_000, seg=70_000)
     shards = [np.ascontiguousarray(data[r * data.size // world:(r + 1) * data.size // world]) for r in range(world)]
     halos = sh2.make_halos(shards, 3_000_000)
-    be = sh2.OracleBackend(1)
+    be = OracleBackend(1)
     region = np.concatenate([shards[rank], halos[rank]])
     ends = sum(s.size for s in shards[rank + 1:]) == halos[rank].size
     out, _ = sh2.compress_sharded(be, sh2.TorchComm(dist), be.load(region), int(shards[rank].size), 1, ends)
