@@ -36,7 +36,7 @@ typedef struct {
 /* ---- a small pool of idle engines: creating one allocates several GB of HBM ---------------- */
 #define POOL_MAX 2
 static pthread_mutex_t pool_mu = PTHREAD_MUTEX_INITIALIZER;
-static struct { bz2b200_engine* e; int level; int device; } pool[POOL_MAX];
+static struct { bz2b200_engine* e; int level; int device; int window_mb; } pool[POOL_MAX];
 
 static int env_int(const char* name, int dflt)
 {
@@ -50,7 +50,7 @@ static int engine_acquire(bz2b200_engine** out, int level)
    int i;
    pthread_mutex_lock(&pool_mu);
    for (i = 0; i < POOL_MAX; i++) {
-      if (pool[i].e && pool[i].level == level && pool[i].device == device) {
+      if (pool[i].e && pool[i].level == level && pool[i].device == device && pool[i].window_mb == env_int("BZ2_B200_WINDOW_MB", 0)) {
          *out = pool[i].e; pool[i].e = NULL;
          pthread_mutex_unlock(&pool_mu);
          return 0;
@@ -67,9 +67,9 @@ static void engine_release(bz2b200_engine* e, int level)
    bz2b200_engine* victim = e;
    pthread_mutex_lock(&pool_mu);
    for (i = 0; i < POOL_MAX; i++) {
-      if (!pool[i].e) { pool[i].e = e; pool[i].level = level; pool[i].device = device; victim = NULL; break; }
+      if (!pool[i].e) { pool[i].e = e; pool[i].level = level; pool[i].device = device; pool[i].window_mb = env_int("BZ2_B200_WINDOW_MB", 0); victim = NULL; break; }
    }
-   if (victim) { victim = pool[0].e; pool[0].e = e; pool[0].level = level; pool[0].device = device; }
+   if (victim) { victim = pool[0].e; pool[0].e = e; pool[0].level = level; pool[0].device = device; pool[0].window_mb = env_int("BZ2_B200_WINDOW_MB", 0); }
    pthread_mutex_unlock(&pool_mu);
    if (victim) bz2b200_engine_destroy(victim);
 }
@@ -153,7 +153,7 @@ int BZ2_bzCompressInit(bz_stream* strm, int blockSize100k, int verbosity, int wo
 {
    cstate* s;
    int rc;
-   (void)verbosity;                                   /* not range-checked here (bzlib.c:155-158) */
+   /* verbosity is not range-checked here (bzlib.c:155-158) */
    if (sizeof(int) != 4 || sizeof(short) != 2 || sizeof(char) != 1) return BZ_CONFIG_ERROR;
    if (strm == NULL || blockSize100k < 1 || blockSize100k > 9 || workFactor < 0 || workFactor > 250)
       return BZ_PARAM_ERROR;
@@ -166,6 +166,7 @@ int BZ2_bzCompressInit(bz_stream* strm, int blockSize100k, int verbosity, int wo
    s->level = blockSize100k;
    rc = engine_acquire(&s->eng, blockSize100k);
    if (rc == 0) rc = bz2b200_stream_begin(s->eng);
+   if (rc == 0) bz2b200_engine_set_verbosity(s->eng, verbosity);
    if (rc) {
       if (s->eng) bz2b200_engine_destroy(s->eng);
       strm->bzfree(strm->opaque, s);
@@ -183,11 +184,15 @@ static int sink_append(void* user, const void* bytes, size_t n)
    cstate* s = (cstate*)user;
    if (s->opos == s->olen) s->opos = s->olen = 0;
    if (s->olen + n > s->ocap) {
+      /* the caller's allocator (bzlib.c:104-115) has no realloc: new buffer, copy, free */
       size_t nc = s->ocap ? s->ocap : (1u << 20);
       unsigned char* nb;
       while (nc < s->olen + n) nc *= 2;
-      nb = (unsigned char*)realloc(s->obuf, nc);
+      if (nc > 0x7fffffffu) return BZ2B200_ENOMEM;
+      nb = (unsigned char*)s->strm->bzalloc(s->strm->opaque, (int)nc, 1);
       if (!nb) return BZ2B200_ENOMEM;
+      if (s->olen) memcpy(nb, s->obuf, s->olen);
+      if (s->obuf) s->strm->bzfree(s->strm->opaque, s->obuf);
       s->obuf = nb; s->ocap = nc;
    }
    memcpy(s->obuf + s->olen, bytes, n);
@@ -295,7 +300,7 @@ int BZ2_bzCompressEnd(bz_stream* strm)
    s = (cstate*)strm->state;
    if (s == NULL || s->strm != strm) return BZ_PARAM_ERROR;
    if (s->eng) engine_release(s->eng, s->level);
-   free(s->obuf);
+   if (s->obuf) strm->bzfree(strm->opaque, s->obuf);
    strm->bzfree(strm->opaque, s);
    strm->state = NULL;
    return BZ_OK;
@@ -325,6 +330,7 @@ int BZ2_bzBuffToBuffCompress(char* dest, unsigned int* destLen, char* source, un
    }
    rc = engine_acquire(&eng, blockSize100k);
    if (rc) return map_engine_error(rc) == BZ_MEM_ERROR ? BZ_MEM_ERROR : BZ_CONFIG_ERROR;
+   bz2b200_engine_set_verbosity(eng, verbosity);
    dlen = *destLen;
    rc = bz2b200_compress_host(eng, source, sourceLen, dest, &dlen, 0, NULL);
    engine_release(eng, blockSize100k);

@@ -60,6 +60,7 @@ void engine_free(EngineFull* e)
    if (e->h_scalars) cudaFreeHost(e->h_scalars);
    if (e->h_counts) cudaFreeHost(e->h_counts);
    if (e->h_blk) cudaFreeHost(e->h_blk);
+   if (e->h_trace) cudaFreeHost(e->h_trace);
    if (e->h_in) cudaFreeHost(e->h_in);
    if (e->h_out) cudaFreeHost(e->h_out);
    if (e->d_in2) cudaFree(e->d_in2);
@@ -92,18 +93,6 @@ int engine_new(EngineFull** out, int device, int level, size_t window_bytes)
    {
       const char* g = getenv("BZ2_B200_S2_GROUP");
       e->s2_group = g ? (u32)atoi(g) : 0;
-      const char* tf = getenv("BZ2_B200_TEXT_FIRST");
-      e->text_first = tf ? (u32)atoi(tf) : 1;
-      const char* pe = getenv("BZ2_B200_PERIODIC");
-      e->periodic = pe ? (u32)atoi(pe) : 1;
-      const char* r8 = getenv("BZ2_B200_RADIX_C8K");
-      e->radix_c8k = r8 ? (u32)atoi(r8) : 1;
-      const char* rx = getenv("BZ2_B200_RADIX_MIN");
-      e->radix_min = rx ? (u32)atoi(rx) : 128;
-      const char* kg = getenv("BZ2_B200_KG_MODE");
-      e->kg_mode = kg ? (u32)atoi(kg) : 1;
-      const char* ss = getenv("BZ2_B200_S2_STREAMS");
-      e->s2_streams = ss ? (u32)atoi(ss) : 1;
       const char* ch = getenv("BZ2_B200_CHAIN");
       e->chain = ch ? (u32)atoi(ch) : 1;
       const char* tf2 = getenv("BZ2_B200_TIE_FORCE");
@@ -181,6 +170,7 @@ int engine_new(EngineFull** out, int device, int level, size_t window_bytes)
       cudaError_t c1 = cudaMallocHost(reinterpret_cast<void**>(&e->h_scalars), 64 * sizeof(u32));
       cudaError_t c2 = cudaMallocHost(reinterpret_cast<void**>(&e->h_counts), 32 * sizeof(u32));
       cudaError_t c3 = cudaMallocHost(reinterpret_cast<void**>(&e->h_blk), (size_t)e->blk_cap * 4 * sizeof(u32) + 64);
+      if (c3 == cudaSuccess) c3 = cudaMallocHost(reinterpret_cast<void**>(&e->h_trace), (size_t)e->blk_cap * sizeof(u32) + 64);
       if (c1 != cudaSuccess || c2 != cudaSuccess || c3 != cudaSuccess) { rc = set_err(BZ2B200_ENOMEM, "pinned host allocation failed"); goto fail; }
    }
    *out = e;
@@ -247,10 +237,24 @@ int run_window(EngineFull* e, const u8* d_in, u32 W, bool is_final, bool tail_me
    BZ_CUDA(e, cudaMemcpyAsync(e->h_blk + e->blk_cap, e->bt.nmtf, sizeof(u32) * nb, cudaMemcpyDeviceToHost, st));
    BZ_CUDA(e, cudaMemcpyAsync(e->h_blk + 2 * (size_t)e->blk_cap, e->bt.power_q, sizeof(u32) * nb, cudaMemcpyDeviceToHost, st));
    BZ_CUDA(e, cudaStreamSynchronize(st));
+   if (e->verbosity >= 2) {
+      // the block sizes and alphabet sizes for the per-block trace lines (compress.c:831-834, :259-262)
+      BZ_CUDA(e, cudaMemcpyAsync(e->h_blk + 3 * (size_t)e->blk_cap, e->bt.X, sizeof(u32) * (nb + 1), cudaMemcpyDeviceToHost, st));
+      BZ_CUDA(e, cudaMemcpyAsync(e->h_trace, e->bt.ninuse, sizeof(u32) * nb, cudaMemcpyDeviceToHost, st));
+      BZ_CUDA(e, cudaStreamSynchronize(st));
+   }
    for (u32 b = 0; b < nb; b++) {
       ss.combined_crc = ((ss.combined_crc << 1) | (ss.combined_crc >> 31)) ^ e->h_blk[b];
       ss.st.sum_nmtf += e->h_blk[e->blk_cap + b];
       if (e->h_blk[2 * (size_t)e->blk_cap + b]) ss.st.n_power_blocks++;
+      if (e->verbosity >= 2) {
+         const u32* X = e->h_blk + 3 * (size_t)e->blk_cap;
+         fprintf(stderr, "    block %d: crc = 0x%08x, combined CRC = 0x%08x, size = %d\n",
+                 (int)(e->trace_block0 + ss.block_no + b + 1), e->h_blk[b], ss.combined_crc, (int)(X[b + 1] - X[b]));
+         if (e->verbosity >= 3)
+            fprintf(stderr, "      %d in block, %d after MTF & 1-2 coding, %d+2 syms in use\n",
+                    (int)(X[b + 1] - X[b]), (int)e->h_blk[e->blk_cap + b], (int)e->h_trace[b]);
+      }
    }
    ss.block_no += nb;
    ss.bits = end_bit;
@@ -343,6 +347,7 @@ static int finish_stream(EngineFull* e, Sink& sk)
 {
    StreamState& ss = e->ss;
    int rc;
+   if (e->verbosity >= 2) fprintf(stderr, "    final combined CRC = 0x%08x\n   ", ss.combined_crc);      // compress.c:877-878
    if ((rc = host_put_bits(e, sk, 0x177245385090ULL, 48))) return rc;     // compress.c:874-875
    if ((rc = host_put_bits(e, sk, ss.combined_crc, 32))) return rc;       // :876
    if (ss.ncarry) { rc = sk.put(&ss.carry, 1); if (rc) return rc; ss.bits += 8 - ss.ncarry; ss.carry = 0; ss.ncarry = 0; }   // :879
@@ -433,7 +438,7 @@ static void* feed_worker(void* arg)
       pthread_mutex_lock(&a.mu);
       if (!a.hook_advanced) a.head += cons;
       a.busy = false;
-      if (rc) a.err = rc;
+      if (rc) { a.err = rc; snprintf(a.errtext, sizeof a.errtext, "%s", g_err[0] ? g_err : e->err); }   // g_err is this thread's copy
       if (closing || rc) a.closing_done = true;
       pthread_cond_broadcast(&a.cv_space);
       pthread_cond_broadcast(&a.cv_done);
@@ -551,6 +556,7 @@ int bz2b200_compress_host(bz2b200_engine* h, const void* src, size_t src_len, vo
    DeviceGuard guard(e->device);
    int rc = ensure_staging(e, false);
    if (rc) return rc;
+   feed_reset(e);                 // a stream abandoned on this (pooled) engine may still have a window in flight
    stream_reset(e);
    Sink sk; sk.fn = nullptr; sk.user = nullptr; sk.dst = static_cast<u8*>(dst); sk.cap = *dst_len; sk.len = 0;
    if ((rc = begin_stream(e, sk))) return rc;
@@ -610,6 +616,7 @@ int bz2b200_compress_device(bz2b200_engine* h, const void* d_src, size_t src_len
    EngineFull* e = reinterpret_cast<EngineFull*>(h);
    if (!e || !d_dst || !dst_len || (!d_src && src_len) || ((uintptr_t)d_dst & 3)) return set_err(BZ2B200_EPARAM, "bad argument");
    DeviceGuard guard(e->device);
+   feed_reset(e);
    e->after_s1 = nullptr;
    stream_reset(e);
    StreamState& ss = e->ss;
@@ -677,7 +684,7 @@ int bz2b200_stream_feed(bz2b200_engine* h, const void* src, size_t n, int end_mo
    while (off < n) {
       pthread_mutex_lock(&a.mu);
       while (!a.err && a.tail - a.head >= a.cap) pthread_cond_wait(&a.cv_space, &a.mu);
-      if (a.err) { rc = a.err; pthread_mutex_unlock(&a.mu); return rc; }
+      if (a.err) { rc = a.err; set_err_text(a.errtext); pthread_mutex_unlock(&a.mu); return rc; }
       const size_t space = a.cap - (size_t)(a.tail - a.head);
       const size_t take = (n - off < space) ? (n - off) : space;
       const size_t pos = (size_t)(a.tail % a.cap);
@@ -703,6 +710,7 @@ int bz2b200_stream_feed(bz2b200_engine* h, const void* src, size_t n, int end_mo
       while (!a.closing_done && !a.err) pthread_cond_wait(&a.cv_done, &a.mu);
       a.pending_end = 0;
       rc = a.err;
+      if (rc) set_err_text(a.errtext);
       pthread_mutex_unlock(&a.mu);
       if (rc) return rc;
    }
@@ -806,6 +814,14 @@ int bz2b200_concat_bits(int device, void* d_dst, uint64_t dst_bit, const void* d
    DeviceGuard guard(device);
    const int rc = concat_bits_device(static_cast<u8*>(d_dst), dst_bit, static_cast<const u8*>(d_src), nbits);
    if (rc) return set_err(BZ2B200_ECUDA, "concat_bits failed");
+   return 0;
+}
+
+int bz2b200_engine_set_verbosity(bz2b200_engine* h, int verbosity)
+{
+   EngineFull* e = reinterpret_cast<EngineFull*>(h);
+   if (!e) return set_err(BZ2B200_EPARAM, "null engine");
+   e->verbosity = verbosity;
    return 0;
 }
 

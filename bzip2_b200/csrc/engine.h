@@ -114,12 +114,6 @@ struct Engine {
    u8  *code;              // [blk_cap*256]
    u32 *kk, *nbins, *hh, *kbits, *ksym;   // [blk_cap]
    u64 *K, *kscrA, *kscrB; // [E] packed text keys; 64-bit key scratch of the large path
-   u32 text_first;         // first refinement round sorts by text keys (default on)
-   u32 periodic;           // resolve tandem-repeat segments in one step (default on)
-   u32 radix_c8k;          // 4097..8192: 1 = shared-memory radix CTA of 1024, 0 = the HBM radix path of the large class
-   u32 radix_min;          // CTA sort classes with at least this many threads use radix passes (1024 = none)
-   u32 kg_mode;            // k-gram bucket sort: 0 = count / rank / atomic scatter, 1 = count with arrival index / place
-   u32 s2_streams;         // run the size classes of a refinement round on side streams (default on)
    u32 chain;              // follow repeat chains: sort a segment by the rank at the end of its chain (default on)
    u32 chain_min_round;    // first refinement round that may use chains
    cudaStream_t aux[3];    // side streams of the BWT rounds
@@ -159,7 +153,10 @@ struct Engine {
    // pinned host mirrors
    u32 *h_scalars;         // [64]
    u32 *h_counts;          // [N_CLASSES]
-   u32 *h_blk;             // [blk_cap*4] per-block results (crc, X, nmtf, power_q)
+   u32 *h_blk;             // [blk_cap*4] per-block results (crc, nmtf, power_q, X)
+   u32 *h_trace;           // [blk_cap] alphabet sizes for the verbosity >= 3 trace
+   int verbosity;          // the reference's trace levels: >= 2 one line per block, >= 3 block statistics (compress.c:831-834, :259-262)
+   u32 trace_block0;       // blocks of the stream handled by other engines before this window (multi.cu)
    u8  *h_in;              // [win_cap] pinned staging for streamed input
    u8  *h_out;             // [out_cap] pinned staging for compressed bytes
 

@@ -32,7 +32,7 @@ struct AsyncFeed {
    u64 head, tail;             // absolute byte counters: the ring holds stream bytes [head, tail)
    int pending_end;            // closing request posted by the feeding thread: 1 = flush, 2 = finish
    bool closing_done, busy, quit, hook_advanced;
-   int err;
+   int err; char errtext[256]; // first failure of the worker and its text (the worker's thread-local message does not travel)
    u8* outq; size_t out_len, out_cap;   // compressed bytes produced by the worker, drained by the feeding thread
 };
 

@@ -56,8 +56,8 @@ struct S2Params {
    u32* ksym;               // [nb] m | bits-per-symbol << 8
    u64* K;                  // [E] packed codes of the next m symbols of every position
    u64* kscrA; u64* kscrB;  // [E] 64-bit key scratch of the large-segment path
-   u32 text_first;          // round 0 sorts by text keys
    u32 debug;
+   u32 kg_agg_alpha;        // count pass aggregates per tile for alphabets up to this size
    u32* nbins;              // [nb] ninuse^k
    const u32* blockmap;
    u32* power_q;
@@ -128,8 +128,11 @@ constexpr int KG_THREADS = 256;
 constexpr int KG_ITEMS = 16;
 constexpr int KG_TILE = KG_THREADS * KG_ITEMS;
 constexpr int KG_MAXK = 24;
+constexpr u32 KG_TAB_LOG2 = 13;             // per-tile k-gram table of the count pass: 8192 slots for 4096 positions
+constexpr u32 KG_TAB = 1u << KG_TAB_LOG2;
+constexpr u32 KG_AGG_MAX_ALPHA = 128;       // aggregate per tile for alphabets up to this size (byte-wide data has few repeats per tile)
 
-enum { KG_HIST = 0, KG_RANK = 1, KG_SCATTER = 2, KG_HISTOFF = 3, KG_PLACE = 4 };
+enum { KG_HISTOFF = 3, KG_PLACE = 4 };
 
 __global__ void __launch_bounds__(KG_THREADS) k_inuse(S2Params p)
 {
@@ -178,22 +181,24 @@ __global__ void __launch_bounds__(256) k_codemap(S2Params p)
    }
 }
 
-template <int MODE>
+template <int MODE, bool AGG>
 __global__ void __launch_bounds__(KG_THREADS) k_kgram(S2Params p)
 {
    __shared__ u8 sc[KG_TILE + 64];
    __shared__ u8 cmap[256];
+   __shared__ u32 tab[AGG ? KG_TAB : 1];
    const u32 b = p.b0 + blockIdx.y;
    const u32 xb = p.X[b], n = p.X[b + 1] - xb;
    const u32 t0 = blockIdx.x * KG_TILE;
    if (t0 >= n) return;
    const u8* T = p.T + xb;
    const u32 k = p.kk[b], base = p.ninuse[b];
+   if (AGG) for (u32 h = threadIdx.x; h < KG_TAB; h += KG_THREADS) tab[h] = 0;
    u32* hist = p.hist + (size_t)(b - p.b0) * p.hist_stride;
    cmap[threadIdx.x] = p.code[(size_t)b * 256 + threadIdx.x];
    __syncthreads();
    const u32 msym = p.ksym[b] & 255u, mbits = p.ksym[b] >> 8;
-   const u32 halo = ((MODE == KG_RANK || MODE == KG_PLACE) && p.text_first) ? max(k, msym) : k;
+   const u32 halo = (MODE == KG_PLACE) ? max(k, msym) : k;
    u32* const koff = reinterpret_cast<u32*>(p.kscrA);
    const u32 span = min((u32)KG_TILE, n - t0) + halo - 1;
    for (u32 s = threadIdx.x; s < span; s += KG_THREADS) {
@@ -202,6 +207,43 @@ __global__ void __launch_bounds__(KG_THREADS) k_kgram(S2Params p)
       sc[s] = cmap[T[gi]];
    }
    __syncthreads();
+   if (AGG && base <= p.kg_agg_alpha) {
+      // Count pass with per-tile aggregation.  10^8 returning global atomics run at the L2's atomic rate (81 G/s, round 1:
+      // 1.25 ms per window) -- but on text only ~22 % of the k-grams of a 4096-position tile are distinct.  The tile first
+      // counts its k-grams in a shared-memory hash table (slot word = key+1 << 13 | count; an element's arrival index
+      // inside the tile is what its shared-memory atomicAdd returns), then issues ONE global atomicAdd per distinct k-gram
+      // for the tile's base inside the bucket.  Order inside a bucket stays irrelevant.
+      u32 slot_loc[KG_ITEMS];
+#pragma unroll
+      for (int it = 0; it < KG_ITEMS; it++) {
+         const u32 s = it * KG_THREADS + threadIdx.x;
+         slot_loc[it] = 0xffffffffu;
+         if (t0 + s < n) {
+            u32 key = 0;
+            for (u32 j = 0; j < k; j++) key = key * base + sc[s + j];
+            const u32 tagw = (key + 1u) << 13;
+            u32 h = (key * 2654435761u) >> (32 - KG_TAB_LOG2);
+            for (;;) {
+               u32 cur = tab[h];
+               if (cur == 0) cur = atomicCAS(&tab[h], 0u, tagw);
+               if (cur == 0 || (cur >> 13) == key + 1u) { slot_loc[it] = (h << 13) | (atomicAdd(&tab[h], 1u) & 0x1fffu); break; }
+               h = (h + 1u) & (KG_TAB - 1u);
+            }
+         }
+      }
+      __syncthreads();
+      for (u32 h = threadIdx.x; h < KG_TAB; h += KG_THREADS) {
+         const u32 w = tab[h];
+         if (w) tab[h] = atomicAdd(&hist[(w >> 13) - 1u], w & 0x1fffu);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int it = 0; it < KG_ITEMS; it++) {
+         const u32 s = it * KG_THREADS + threadIdx.x;
+         if (slot_loc[it] != 0xffffffffu) koff[xb + t0 + s] = tab[slot_loc[it] >> 13] + (slot_loc[it] & 0x1fffu);
+      }
+      return;
+   }
 #pragma unroll 2
    for (int it = 0; it < KG_ITEMS; it++) {
       const u32 s = it * KG_THREADS + threadIdx.x;
@@ -209,19 +251,15 @@ __global__ void __launch_bounds__(KG_THREADS) k_kgram(S2Params p)
       if (i < n) {
          u32 key = 0;
          for (u32 j = 0; j < k; j++) key = key * base + sc[s + j];
-         if (MODE == KG_HIST) atomicAdd(&hist[key], 1u);
-         else if (MODE == KG_HISTOFF) koff[xb + i] = atomicAdd(&hist[key], 1u);     // arrival order inside the bucket
-         else if (MODE == KG_RANK || MODE == KG_PLACE) {
+         if (MODE == KG_HISTOFF) koff[xb + i] = atomicAdd(&hist[key], 1u);          // arrival order inside the bucket
+         else {
             const u32 start = hist[key];
             p.rank[xb + i] = rk_pack(0xffffu, 0, start);
-            if (MODE == KG_PLACE) p.sa[xb + start + koff[xb + i]] = i;
-            if (p.text_first) {
-               u64 kw = 0;
-               for (u32 j = 0; j < msym; j++) kw = (kw << mbits) | (u64)sc[s + j];
-               p.K[xb + i] = kw;
-            }
+            p.sa[xb + start + koff[xb + i]] = i;
+            u64 kw = 0;
+            for (u32 j = 0; j < msym; j++) kw = (kw << mbits) | (u64)sc[s + j];
+            p.K[xb + i] = kw;
          }
-         else { const u32 pos = atomicAdd(&hist[key], 1u); p.sa[xb + pos] = i; }
       }
    }
 }
@@ -259,8 +297,7 @@ __global__ void __launch_bounds__(1024) k_kgram_scan(S2Params p)
    }
 }
 
-// after the scatter hist[bin] is the END of bucket `bin`; emit the initial segments
-template <bool ENDS>
+// hist[bin] is the start of bucket `bin` (k_kgram_scan); emit the initial segments
 __global__ void __launch_bounds__(256) k_seg_init(S2Params p, ListsDev L)
 {
    const u32 b = p.b0 + blockIdx.y;
@@ -268,9 +305,8 @@ __global__ void __launch_bounds__(256) k_seg_init(S2Params p, ListsDev L)
    const u32* hist = p.hist + (size_t)(b - p.b0) * p.hist_stride;
    const u32 bin = blockIdx.x * 256 + threadIdx.x;
    const bool vbin = bin < p.nbins[b];
-   // ENDS: the scatter pass left hist[bin] = end of the bucket; otherwise hist[bin] is still its start
-   const u32 end = !vbin ? 0 : ENDS ? hist[bin] : (bin + 1 < p.nbins[b] ? hist[bin + 1] : n);
-   const u32 start = !vbin ? 0 : ENDS ? (bin ? hist[bin - 1] : 0) : hist[bin];
+   const u32 end = !vbin ? 0 : (bin + 1 < p.nbins[b] ? hist[bin + 1] : n);
+   const u32 start = !vbin ? 0 : hist[bin];
    const u32 len = end - start;
    const bool multi = vbin && len >= 2;
    const bool deep = (p.kk[b] >= n);                  // depth k already covers the whole rotation
@@ -288,7 +324,6 @@ template <> struct KeyOf<true> { typedef u64 type; };
 __device__ __forceinline__ u32 round_shift(const S2Params& p, u32 b, u32 round, u32* depth_after)
 {
    const u32 k = p.kk[b];
-   if (!p.text_first) { const u32 sft = k << round; *depth_after = 2u * sft; return sft; }
    if (round == 0) { *depth_after = p.hh[b]; return k; }
    const u32 sft = p.hh[b] << (round - 1);
    *depth_after = 2u * sft;
@@ -296,10 +331,10 @@ __device__ __forceinline__ u32 round_shift(const S2Params& p, u32 b, u32 round, 
 }
 
 template <bool TEXT>
-__device__ __forceinline__ typename KeyOf<TEXT>::type load_key(const S2Params& p, u32 xb, u32 n, u32 idx, u32 shift, u32 tag)
+__device__ __forceinline__ typename KeyOf<TEXT>::type load_key(const S2Params& p, u32 xb, u32 n, u32 idx, u32 shift, u32 tag, u32 ks)
 {
    u32 t = idx + shift; if (t >= n) t -= n;
-   if (TEXT) return (typename KeyOf<TEXT>::type)p.K[xb + t];
+   if (TEXT) return (typename KeyOf<TEXT>::type)p.K[xb + t];        // (keys rebuilt from a 1-byte code text were measured: 3 % slower)
    if (p.jd) { t += p.jd[xb + idx]; if (t >= n) t -= n; }      // key at the end of the segment's repeat chain (2e)
    return (typename KeyOf<TEXT>::type)rk_read(p.rank[xb + t], tag);
 }
@@ -365,7 +400,7 @@ __global__ void __launch_bounds__(256) k_refine_small(S2Params p, ListsDev Lout,
    KT key = ~(KT)0;
    if (active) idx = p.sa[pos + sub];
    if (TEXT) {
-      if (active) key = load_key<TEXT>(p, xb, n, idx, shift, round + 1);
+      if (active) key = load_key<TEXT>(p, xb, n, idx, shift, round + 1, p.ksym[b]);
    } else {
       const u32 head_lane = lane_id() & ~(u32)(LANES - 1);
       const u32 gm = (LANES == 32) ? FULL : (((1u << (LANES & 31)) - 1u) << head_lane);
@@ -522,6 +557,7 @@ k_refine_medium(S2Params p, ListsDev Lout, const u64* items, u32 count, u32 roun
    if (len == 0 && (WARP || vseg)) return;               // resolved by k_resolve_periodic (warp- resp. CTA-uniform)
    u32 xb = 0, n = 1, shift = 0, depth = 0;
    if (vseg) { xb = p.X[b]; n = p.X[b + 1] - xb; shift = round_shift(p, b, round, &depth); }
+   const u32 ks = (TEXT && vseg) ? p.ksym[b] : 0;
    u32 n2 = 64;
    while (n2 < len) n2 <<= 1;
    // blocked load: thread t owns sequence positions t*8 .. t*8+7; the element's local id travels
@@ -533,7 +569,7 @@ k_refine_medium(S2Params p, ListsDev Lout, const u64* items, u32 count, u32 roun
       VT w = ~(VT)0;
       if (i < len) {
          const u32 idx = p.sa[pos + i];
-         w = (load_key<TEXT>(p, xb, n, idx, shift, round + 1) << MS_LBITS) | (VT)i;
+         w = (load_key<TEXT>(p, xb, n, idx, shift, round + 1, ks) << MS_LBITS) | (VT)i;
       }
       v[r] = w;
    }
@@ -634,6 +670,7 @@ __global__ void __launch_bounds__(THREADS) k_refine_radix(S2Params p, ListsDev L
    const u32 xb = p.X[b], n = p.X[b + 1] - xb;
    u32 depth;
    const u32 shift = round_shift(p, b, round, &depth);
+   const u32 ks = TEXT ? p.ksym[b] : 0;
 
    // striped load: warp w owns positions w*256 .. w*256+255, lane l takes every 32nd of them
    VT v[MS_ITEMS];
@@ -644,7 +681,7 @@ __global__ void __launch_bounds__(THREADS) k_refine_radix(S2Params p, ListsDev L
       VT word = ~(VT)0;
       if (i < len) {
          const u32 idx = p.sa[pos + i];
-         word = ((VT)load_key<TEXT>(p, xb, n, idx, shift, round + 1) << LBITS) | (VT)i;
+         word = ((VT)load_key<TEXT>(p, xb, n, idx, shift, round + 1, ks) << LBITS) | (VT)i;
          vand &= word; vor |= word;
       }
       v[k] = word;
@@ -799,6 +836,7 @@ __global__ void __launch_bounds__(LG_THREADS, 1024 / LG_THREADS) k_refine_large(
    const u32 xb = p.X[b], n = p.X[b + 1] - xb;
    u32 depth;
    const u32 shift0 = round_shift(p, b, round, &depth);
+   const u32 ks = TEXT ? p.ksym[b] : 0;
    const int npass = TEXT ? (int)((p.kbits[b] + 7) >> 3) : ((n > 65536u) ? 3 : 2);
    KT* const kA = TEXT ? reinterpret_cast<KT*>(p.kscrA) : reinterpret_cast<KT*>(p.keyA);
    KT* const kB = TEXT ? reinterpret_cast<KT*>(p.kscrB) : reinterpret_cast<KT*>(p.keyB);
@@ -809,7 +847,7 @@ __global__ void __launch_bounds__(LG_THREADS, 1024 / LG_THREADS) k_refine_large(
    // phase A: gather keys, digit histograms
    for (u32 i = threadIdx.x; i < len; i += LG_THREADS) {
       const u32 idx = p.sa[pos + i];
-      const KT key = load_key<TEXT>(p, xb, n, idx, shift0, round + 1);
+      const KT key = load_key<TEXT>(p, xb, n, idx, shift0, round + 1, ks);
       kA[pos + i] = key;
       for (int q = 0; q < npass; q++) atomicAdd(&binbase[q][(u32)(key >> (8 * q)) & 255], 1u);
    }
@@ -1393,8 +1431,8 @@ int stage2_run(Engine* e, u32 nb, u32 E)
    p.keyA = e->keyA; p.keyB = e->keyB; p.idxB = e->idxB;
    p.hist = e->hist; p.hist_stride = e->hist_stride; p.code = e->code; p.kk = e->kk; p.nbins = e->nbins;
    p.hh = e->hh; p.kbits = e->kbits; p.ksym = e->ksym; p.K = e->K; p.kscrA = e->kscrA; p.kscrB = e->kscrB;
-   p.text_first = e->text_first;
    p.debug = trace_on() ? 1 : 0;
+   { static int agg = -1; if (agg < 0) { const char* v = getenv("BZ2_B200_KG_AGG"); agg = v ? atoi(v) : (int)KG_AGG_MAX_ALPHA; } p.kg_agg_alpha = (u32)agg; }
    p.blockmap = e->blockmap;
    p.power_q = e->bt.power_q; p.inuse = e->bt.inuse; p.ninuse = e->bt.ninuse;
    p.jd = nullptr; p.jq = nullptr; p.dstar = nullptr;
@@ -1415,20 +1453,14 @@ int stage2_run(Engine* e, u32 nb, u32 E)
       const dim3 gtiles((max_n + KG_TILE - 1) / KG_TILE, g);
       k_inuse<<<gtiles, KG_THREADS, 0, st>>>(p);                                                BZ_KCHECK(e);
       k_codemap<<<g, 256, 0, st>>>(p);                                                          BZ_KCHECK(e);
-      if (e->kg_mode == 0) {
-         k_kgram<KG_HIST><<<gtiles, KG_THREADS, 0, st>>>(p);                                       BZ_KCHECK(e);
-         k_kgram_scan<<<g, 1024, 0, st>>>(p);                                                      BZ_KCHECK(e);
-         k_kgram<KG_RANK><<<gtiles, KG_THREADS, 0, st>>>(p);                                       BZ_KCHECK(e);
-         k_kgram<KG_SCATTER><<<gtiles, KG_THREADS, 0, st>>>(p);                                    BZ_KCHECK(e);
-         k_seg_init<true><<<dim3((e->hist_stride + 255) / 256, g), 256, 0, st>>>(p, lists_dev(e, 0)); BZ_KCHECK(e);
-      } else {
-         // one atomic pass: the count pass keeps each rotation's arrival index inside its bucket, so the
-         // placement pass needs no atomics (bucket start + arrival index)
-         k_kgram<KG_HISTOFF><<<gtiles, KG_THREADS, 0, st>>>(p);                                    BZ_KCHECK(e);
-         k_kgram_scan<<<g, 1024, 0, st>>>(p);                                                      BZ_KCHECK(e);
-         k_kgram<KG_PLACE><<<gtiles, KG_THREADS, 0, st>>>(p);                                      BZ_KCHECK(e);
-         k_seg_init<false><<<dim3((e->hist_stride + 255) / 256, g), 256, 0, st>>>(p, lists_dev(e, 0)); BZ_KCHECK(e);
-      }
+      // one atomic pass: the count pass keeps each rotation's arrival index inside its bucket, so the
+      // placement pass needs no atomics (bucket start + arrival index)
+      if (p.kg_agg_alpha) k_kgram<KG_HISTOFF, true><<<gtiles, KG_THREADS, 0, st>>>(p);
+      else                k_kgram<KG_HISTOFF, false><<<gtiles, KG_THREADS, 0, st>>>(p);
+      BZ_KCHECK(e);
+      k_kgram_scan<<<g, 1024, 0, st>>>(p);                                                      BZ_KCHECK(e);
+      k_kgram<KG_PLACE, false><<<gtiles, KG_THREADS, 0, st>>>(p);                                      BZ_KCHECK(e);
+      k_seg_init<<<dim3((e->hist_stride + 255) / 256, g), 256, 0, st>>>(p, lists_dev(e, 0));    BZ_KCHECK(e);
       dbg_sync(e, "k-gram phase");
 
       int cur = 0;
@@ -1467,7 +1499,7 @@ int stage2_run(Engine* e, u32 nb, u32 E)
          ListsDev Lout = lists_dev(e, nxt);
          u32** si = e->lists.small_items[cur];
          u64** bi = e->lists.big_items[cur];
-         const bool text = (round == 0) && e->text_first;
+         const bool text = (round == 0);
          // The size classes of one round touch disjoint segments, so they run side by side: the few
          // long-running CTAs of the large and CTA-sort classes overlap the sub-warp classes' tails.
          // tandem repeats: the large class from round 0 on (few segments), every CTA/warp-sorted class from round 2 on
@@ -1481,7 +1513,7 @@ int stage2_run(Engine* e, u32 nb, u32 E)
          const bool chain_ok = e->chain && !text && round >= 1;
          const bool force = e->chain >= 2;                                      // BZ2_B200_CHAIN=2: always (tests)
          const bool go_small = chain_ok && round >= e->chain_min_round && (force || (est_small >= E / 32 && est_small * 10 >= prev_small * 6));
-         const bool go_big = chain_ok && e->periodic && (force || (est_big >= E / 32 && est_big * 10 >= prev_big * 6));
+         const bool go_big = chain_ok && (force || (est_big >= E / 32 && est_big * 10 >= prev_big * 6));
          prev_small = est_small; prev_big = est_big;
          ApLists AL;
          u32 ap_tot = 0;
@@ -1527,11 +1559,11 @@ int stage2_run(Engine* e, u32 nb, u32 E)
                dbg_sync(e, "repeat chains");
             }
          }
-         if (e->periodic && ap_tot) {
+         if (ap_tot) {
             k_resolve_periodic<<<ap_tot, AP_THREADS, 0, st>>>(p, AL, round); BZ_KCHECK(e);
             dbg_sync(e, "k_resolve_periodic");
          }
-         const bool fork = e->s2_streams && total > 64;
+         const bool fork = total > 64;
          cudaStream_t sL = st, sM = st, sW = st;
          if (fork) {
             sL = e->aux[0]; sM = e->aux[1]; sW = e->aux[2];
@@ -1542,15 +1574,12 @@ int stage2_run(Engine* e, u32 nb, u32 E)
             launch_large(e, sL, p, Lout, bi[6], cnt[CLS_LARGE], round, text);
             dbg_sync(e, "k_refine_large");
          }
-         if (cnt[CLS_C8K]) {
-            if (e->radix_c8k) launch_radix<1024>(e, sL, p, Lout, bi[5], cnt[CLS_C8K], round, text);
-            else launch_large(e, sL, p, Lout, bi[5], cnt[CLS_C8K], round, text);
-         }
-         const u32 rx = e->radix_min;            // smallest CTA class sorted by radix passes instead of the bitonic network
-         if (cnt[CLS_C4K])   { if (rx <= 512) launch_radix<512>(e, sM, p, Lout, bi[4], cnt[CLS_C4K], round, text); else launch_medium<512>(e, sM, p, Lout, bi[4], cnt[CLS_C4K], round, text); }
-         if (cnt[CLS_C2K])   { if (rx <= 256) launch_radix<256>(e, sM, p, Lout, bi[3], cnt[CLS_C2K], round, text); else launch_medium<256>(e, sM, p, Lout, bi[3], cnt[CLS_C2K], round, text); }
-         if (cnt[CLS_C1K])   { if (rx <= 128) launch_radix<128>(e, sW, p, Lout, bi[2], cnt[CLS_C1K], round, text); else launch_medium<128>(e, sW, p, Lout, bi[2], cnt[CLS_C1K], round, text); }
-         if (cnt[CLS_C512])  { if (rx <= 64)  launch_radix<64>(e, sW, p, Lout, bi[1], cnt[CLS_C512], round, text);  else launch_medium<64>(e, sW, p, Lout, bi[1], cnt[CLS_C512], round, text); }
+         // 513..8192: shared-memory radix CTAs; 257..512: the packed-word bitonic CTA of 64 (both measured against each other in round 1)
+         if (cnt[CLS_C8K])   launch_radix<1024>(e, sL, p, Lout, bi[5], cnt[CLS_C8K], round, text);
+         if (cnt[CLS_C4K])   launch_radix<512>(e, sM, p, Lout, bi[4], cnt[CLS_C4K], round, text);
+         if (cnt[CLS_C2K])   launch_radix<256>(e, sM, p, Lout, bi[3], cnt[CLS_C2K], round, text);
+         if (cnt[CLS_C1K])   launch_radix<128>(e, sW, p, Lout, bi[2], cnt[CLS_C1K], round, text);
+         if (cnt[CLS_C512])  launch_medium<64>(e, sW, p, Lout, bi[1], cnt[CLS_C512], round, text);
          if (cnt[CLS_W256])  launch_medium<32>(e, sW, p, Lout, bi[0], cnt[CLS_W256], round, text);
          if (cnt[4]) launch_small<32>(e, st, p, Lout, si[4], cnt[4], round, text);
          if (cnt[3]) launch_small<16>(e, st, p, Lout, si[3], cnt[3], round, text);

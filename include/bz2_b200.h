@@ -75,6 +75,11 @@ void bz2b200_engine_destroy(bz2b200_engine* e);
 /* Run on the caller's CUDA stream (a cudaStream_t); NULL restores the engine's own stream. */
 int  bz2b200_engine_set_stream(bz2b200_engine* e, void* cuda_stream);
 
+/* The reference's `verbosity` (bzlib.c:144; 0-4): at >= 2 one line per block with its CRC, the combined CRC and its
+ * size, and the final combined CRC; at >= 3 also nblock / nMTF / symbols in use -- same text as compress.c:831-834,
+ * :259-262, :877-878, on stderr.  (The per-pass coding-table statistics of compress.c:304-308, :544-550 are not kept.) */
+int  bz2b200_engine_set_verbosity(bz2b200_engine* e, int verbosity);
+
 /* Whole-stream compression, host buffers.  *dst_len: capacity in, bytes written out. */
 int  bz2b200_compress_host(bz2b200_engine* e, const void* src, size_t src_len,
                            void* dst, size_t* dst_len, unsigned flags, bz2b200_stats* stats);

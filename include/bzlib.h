@@ -7,7 +7,13 @@
  * codes and the bz_stream layout are the reference's, so existing callers
  * relink unchanged; the work behind them runs on the GPU (see bz2_b200.h).
  * Decompression entry points are provided by a small host decoder (used for
- * round-trip checks); they are outside the accelerated path.
+ * round-trip checks); they are outside the accelerated path.  It does not decode
+ * the "randomised" blocks that only pre-0.9.5 encoders wrote (BZ_DATA_ERROR).
+ *
+ * Memory: the stream state and the queue of compressed bytes waiting for the caller
+ * are obtained through bzalloc / bzfree (bzlib.c:104-115, :164-175).  Device memory
+ * and the pinned staging buffers of the engine cannot be: they come from the CUDA
+ * driver (cudaMalloc / cudaMallocHost).
  */
 #ifndef BZ2_B200_BZLIB_H
 #define BZ2_B200_BZLIB_H
@@ -18,16 +24,26 @@
 extern "C" {
 #endif
 
-/* actions for BZ2_bzCompress */
-enum { BZ_RUN = 0, BZ_FLUSH = 1, BZ_FINISH = 2 };
+/* actions for BZ2_bzCompress and return codes: preprocessor constants, as in the reference (bzlib.h:29-46), so that
+ * clients testing them with #ifdef / #if compile unchanged */
+#define BZ_RUN               0
+#define BZ_FLUSH             1
+#define BZ_FINISH            2
 
-/* return codes */
-enum {
-   BZ_OK = 0, BZ_RUN_OK = 1, BZ_FLUSH_OK = 2, BZ_FINISH_OK = 3, BZ_STREAM_END = 4,
-   BZ_SEQUENCE_ERROR = -1, BZ_PARAM_ERROR = -2, BZ_MEM_ERROR = -3, BZ_DATA_ERROR = -4,
-   BZ_DATA_ERROR_MAGIC = -5, BZ_IO_ERROR = -6, BZ_UNEXPECTED_EOF = -7,
-   BZ_OUTBUFF_FULL = -8, BZ_CONFIG_ERROR = -9
-};
+#define BZ_OK                0
+#define BZ_RUN_OK            1
+#define BZ_FLUSH_OK          2
+#define BZ_FINISH_OK         3
+#define BZ_STREAM_END        4
+#define BZ_SEQUENCE_ERROR    (-1)
+#define BZ_PARAM_ERROR       (-2)
+#define BZ_MEM_ERROR         (-3)
+#define BZ_DATA_ERROR        (-4)
+#define BZ_DATA_ERROR_MAGIC  (-5)
+#define BZ_IO_ERROR          (-6)
+#define BZ_UNEXPECTED_EOF    (-7)
+#define BZ_OUTBUFF_FULL      (-8)
+#define BZ_CONFIG_ERROR      (-9)
 
 #define BZ_MAX_UNUSED 5000
 

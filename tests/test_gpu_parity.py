@@ -377,6 +377,49 @@ def test_two_streams_on_two_threads(engine_for):
     assert got[0] == exps[0] and got[1] == exps[1]
 
 
+def test_custom_allocator_is_used_and_balanced():
+    """bzalloc / bzfree (bzlib.c:104-115): the stream state and the queue of pending output go through the caller's
+    allocator, and everything obtained is given back by BZ2_bzCompressEnd."""
+    lib = B.load()
+    live, sizes = {}, []
+    ALLOC = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_int, C.c_int)
+    FREE = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)
+    libc = C.CDLL(None)
+    libc.malloc.restype = C.c_void_p
+    libc.malloc.argtypes = [C.c_size_t]
+    libc.free.argtypes = [C.c_void_p]
+
+    def alloc(opaque, items, size):
+        p = libc.malloc(items * size)
+        live[p] = items * size
+        sizes.append(items * size)
+        return p
+
+    def free(opaque, p):
+        if p:
+            assert p in live
+            del live[p]
+            libc.free(p)
+    a_cb, f_cb = ALLOC(alloc), FREE(free)
+    strm = binding.BzStream()
+    strm.bzalloc = C.cast(a_cb, C.c_void_p)
+    strm.bzfree = C.cast(f_cb, C.c_void_p)
+    assert lib.BZ2_bzCompressInit(C.byref(strm), 9, 0, 0) == binding.BZ_OK
+    d = S.gen_random(3_000_000)
+    out = np.empty(4_000_000, np.uint8)
+    strm.next_in, strm.avail_in = d.ctypes.data, d.size
+    strm.next_out, strm.avail_out = out.ctypes.data, 1000          # a small output window: the rest waits in the queue
+    rc = lib.BZ2_bzCompress(C.byref(strm), binding.BZ_FINISH)
+    assert rc == binding.BZ_FINISH_OK
+    strm.avail_out = out.size - 1000
+    assert lib.BZ2_bzCompress(C.byref(strm), binding.BZ_FINISH) == binding.BZ_STREAM_END
+    n = out.size - strm.avail_out
+    assert bz2.decompress(out[:n].tobytes()) == d.tobytes()
+    assert len(sizes) >= 2 and max(sizes) >= 1 << 20               # the state and the output queue
+    assert lib.BZ2_bzCompressEnd(C.byref(strm)) == binding.BZ_OK
+    assert not live
+
+
 def test_outbuff_full():
     lib = B.load()
     d = S.gen_random(50_000)

@@ -82,6 +82,12 @@ def test_reference_cli_relinked(tmp_path, level):
     # and the reference decodes it
     dec = subprocess.run([REF_CLI, "-dc", str(tmp_path / "input.dat.bz2")], capture_output=True)
     assert dec.returncode == 0 and dec.stdout == data
+    # -vv: the library's per-block trace (compress.c:831-834, :877-878) is the reference's, line for line
+    tr_ref = subprocess.run([REF_CLI, f"-{level}", "-vv", "-c", str(src)], capture_output=True)
+    tr_ours = subprocess.run([RELINKED, f"-{level}", "-vv", "-c", str(src)], capture_output=True)
+    pick = lambda err: [ln for ln in err.decode().splitlines() if ln.startswith("    block ") or "final combined CRC" in ln]
+    assert tr_ours.stdout == ref.stdout
+    assert len(pick(tr_ref.stderr)) >= 3 and pick(tr_ours.stderr) == pick(tr_ref.stderr)
 
 
 @pytest.mark.skipif(not os.path.exists(REF_CLI), reason="oracle/_ref/bzip2_ref not shipped")

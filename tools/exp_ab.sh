@@ -1,11 +1,11 @@
 #!/bin/bash
-# scratch experiment driver; results land in gpurun_out/
-set -u
-cd "${GRAFT_REPO_ROOT:-/root/repo}"
-O=gpurun_out
-rm -f $O/ab.log
-python -m pytest tests -x -q -m gpu --timeout 1200 > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/ab.log
-for wl in text random period1000; do
-  echo "== $wl" >> $O/ab.log
-  python bench.py --mb 400 --steps 3 --warmup 2 --no-e2e --no-cpu --workload $wl >> $O/ab.log 2>&1
+# A/B of one environment switch inside one box: tools/exp_ab.sh VAR A B [bench args...]
+VAR=$1; A=$2; B=$3; shift 3
+for rep in 1 2; do
+  for V in $A $B; do
+    env $VAR=$V python bench.py --steps 4 --warmup 2 --no-c4 --no-cpu "$@" 2>/dev/null | tail -1 | python -c "
+import json,sys
+l=json.loads(sys.stdin.read())
+print('$VAR=$V', 'value', l['value'], 'ms', l['ms_per_step'], 'e2e', (l['e2e'] or {}).get('value'), 's2(one engine)', l['roofline']['stage_ms']['s2_bwt'])"
+  done
 done
