@@ -42,7 +42,7 @@ def build_library(verbose=False):
 EXPORTS = [
     # include/bz2_b200.h
     "bz2b200_device_count", "bz2b200_last_error", "bz2b200_version", "bz2b200_engine_create",
-    "bz2b200_engine_destroy", "bz2b200_engine_set_stream", "bz2b200_engine_set_verbosity", "bz2b200_compress_host", "bz2b200_compress_device", "bz2b200_stream_begin",
+    "bz2b200_engine_create_bounded", "bz2b200_engine_destroy", "bz2b200_engine_set_stream", "bz2b200_engine_set_verbosity", "bz2b200_compress_host", "bz2b200_compress_device", "bz2b200_stream_begin",
     "bz2b200_stream_feed", "bz2b200_debug_keep", "bz2b200_debug_fetch",
     "bz2b200_scan_create", "bz2b200_scan_rescan", "bz2b200_scan_boundary", "bz2b200_scan_destroy", "bz2b200_concat_bits",
     "bz2b200_multi_create", "bz2b200_multi_destroy", "bz2b200_multi_engines", "bz2b200_multi_compress",

@@ -34,7 +34,8 @@ typedef struct {
 } cstate;
 
 /* ---- a small pool of idle engines: creating one allocates several GB of HBM ---------------- */
-#define POOL_MAX 2
+#define POOL_MAX 3
+#define SMALL_INPUT ((size_t)8 << 20)      /* one-shot calls up to this size use an engine sized to the input */
 static pthread_mutex_t pool_mu = PTHREAD_MUTEX_INITIALIZER;
 static struct { bz2b200_engine* e; int level; int device; int window_mb; } pool[POOL_MAX];
 
@@ -44,32 +45,42 @@ static int env_int(const char* name, int dflt)
    return (v && *v) ? atoi(v) : dflt;
 }
 
-static int engine_acquire(bz2b200_engine** out, int level)
+/* window key of the pool: the configured window in MB, or -k for an engine bounded to inputs of at most k MiB */
+static int window_key(size_t bounded_bytes)
+{
+   if (bounded_bytes) { int k = 1; while (((size_t)k << 20) < bounded_bytes) k <<= 1; return -k; }
+   return env_int("BZ2_B200_WINDOW_MB", 0);
+}
+
+static int engine_acquire(bz2b200_engine** out, int level, size_t bounded_bytes)
 {
    const int device = env_int("BZ2_B200_DEVICE", 0);
+   const int wkey = window_key(bounded_bytes);
    int i;
    pthread_mutex_lock(&pool_mu);
    for (i = 0; i < POOL_MAX; i++) {
-      if (pool[i].e && pool[i].level == level && pool[i].device == device && pool[i].window_mb == env_int("BZ2_B200_WINDOW_MB", 0)) {
+      if (pool[i].e && pool[i].level == level && pool[i].device == device && pool[i].window_mb == wkey) {
          *out = pool[i].e; pool[i].e = NULL;
          pthread_mutex_unlock(&pool_mu);
          return 0;
       }
    }
    pthread_mutex_unlock(&pool_mu);
-   return bz2b200_engine_create(out, device, level, (size_t)env_int("BZ2_B200_WINDOW_MB", 0) << 20);
+   if (wkey < 0) return bz2b200_engine_create_bounded(out, device, level, (size_t)(-wkey) << 20);
+   return bz2b200_engine_create(out, device, level, (size_t)wkey << 20);
 }
 
-static void engine_release(bz2b200_engine* e, int level)
+static void engine_release(bz2b200_engine* e, int level, size_t bounded_bytes)
 {
    const int device = env_int("BZ2_B200_DEVICE", 0);
+   const int wkey = window_key(bounded_bytes);
    int i;
    bz2b200_engine* victim = e;
    pthread_mutex_lock(&pool_mu);
    for (i = 0; i < POOL_MAX; i++) {
-      if (!pool[i].e) { pool[i].e = e; pool[i].level = level; pool[i].device = device; pool[i].window_mb = env_int("BZ2_B200_WINDOW_MB", 0); victim = NULL; break; }
+      if (!pool[i].e) { pool[i].e = e; pool[i].level = level; pool[i].device = device; pool[i].window_mb = wkey; victim = NULL; break; }
    }
-   if (victim) { victim = pool[0].e; pool[0].e = e; pool[0].level = level; pool[0].device = device; pool[0].window_mb = env_int("BZ2_B200_WINDOW_MB", 0); }
+   if (victim) { victim = pool[0].e; pool[0].e = e; pool[0].level = level; pool[0].device = device; pool[0].window_mb = wkey; }
    pthread_mutex_unlock(&pool_mu);
    if (victim) bz2b200_engine_destroy(victim);
 }
@@ -164,7 +175,7 @@ int BZ2_bzCompressInit(bz_stream* strm, int blockSize100k, int verbosity, int wo
    memset(s, 0, sizeof *s);
    s->strm = strm;
    s->level = blockSize100k;
-   rc = engine_acquire(&s->eng, blockSize100k);
+   rc = engine_acquire(&s->eng, blockSize100k, 0);
    if (rc == 0) rc = bz2b200_stream_begin(s->eng);
    if (rc == 0) bz2b200_engine_set_verbosity(s->eng, verbosity);
    if (rc) {
@@ -299,7 +310,7 @@ int BZ2_bzCompressEnd(bz_stream* strm)
    if (strm == NULL) return BZ_PARAM_ERROR;
    s = (cstate*)strm->state;
    if (s == NULL || s->strm != strm) return BZ_PARAM_ERROR;
-   if (s->eng) engine_release(s->eng, s->level);
+   if (s->eng) engine_release(s->eng, s->level, 0);
    if (s->obuf) strm->bzfree(strm->opaque, s->obuf);
    strm->bzfree(strm->opaque, s);
    strm->state = NULL;
@@ -328,12 +339,16 @@ int BZ2_bzBuffToBuffCompress(char* dest, unsigned int* destLen, char* source, un
          return BZ_OK;
       }
    }
-   rc = engine_acquire(&eng, blockSize100k);
-   if (rc) return map_engine_error(rc) == BZ_MEM_ERROR ? BZ_MEM_ERROR : BZ_CONFIG_ERROR;
-   bz2b200_engine_set_verbosity(eng, verbosity);
-   dlen = *destLen;
-   rc = bz2b200_compress_host(eng, source, sourceLen, dest, &dlen, 0, NULL);
-   engine_release(eng, blockSize100k);
+   {
+      /* a small input gets an engine sized to it (a few hundred MB of HBM instead of ~9 GB) */
+      const size_t bounded = (sourceLen <= SMALL_INPUT) ? (sourceLen ? sourceLen : 1) : 0;
+      rc = engine_acquire(&eng, blockSize100k, bounded);
+      if (rc) return map_engine_error(rc) == BZ_MEM_ERROR ? BZ_MEM_ERROR : BZ_CONFIG_ERROR;
+      bz2b200_engine_set_verbosity(eng, verbosity);
+      dlen = *destLen;
+      rc = bz2b200_compress_host(eng, source, sourceLen, dest, &dlen, 0, NULL);
+      engine_release(eng, blockSize100k, bounded);
+   }
    if (rc == BZ2B200_EOUTFULL) return BZ_OUTBUFF_FULL;
    if (rc) return map_engine_error(rc);
    *destLen = (unsigned int)dlen;

@@ -73,7 +73,7 @@ void engine_free(EngineFull* e)
    free(e);
 }
 
-int engine_new(EngineFull** out, int device, int level, size_t window_bytes)
+int engine_new(EngineFull** out, int device, int level, size_t window_bytes, bool bounded)
 {
    int ndev = 0;
    cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -102,7 +102,9 @@ int engine_new(EngineFull** out, int device, int level, size_t window_bytes)
    }
    if (window_bytes == 0) window_bytes = (size_t)96 << 20;
    // a window must be able to hold the input of one full block of pure runs (255 -> 5 bytes)
-   const size_t min_win = (size_t)(e->nmax + 16) * 52;
+   // ... unless the caller bounds the whole input (one-shot calls on small inputs): then the input itself is the window
+   const size_t min_win = bounded ? ((size_t)64 << 10) : (size_t)(e->nmax + 16) * 52;
+   e->bounded = bounded;
    if (window_bytes < min_win) window_bytes = min_win;
    if (window_bytes > ((size_t)100 << 20)) window_bytes = (size_t)100 << 20;   // 1.25*W must stay below 2^27
    e->win_cap = (u32)window_bytes;
@@ -125,6 +127,7 @@ int engine_new(EngineFull** out, int device, int level, size_t window_bytes)
       if (stage2_init() != 0) { rc = engine_fail(e, cudaGetLastError(), __FILE__, __LINE__); goto fail; }
       c0 = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
       if (c0 == cudaSuccess) c0 = cudaEventCreateWithFlags(&e->ev_s1, cudaEventDisableTiming);
+      if (c0 == cudaSuccess) c0 = cudaEventCreateWithFlags(&e->ev_s1b, cudaEventDisableTiming);
       if (c0 != cudaSuccess) { rc = engine_fail(e, c0, __FILE__, __LINE__); goto fail; }
       ALLOC(e->enc, E + 64); ALLOC(e->cend, E + 64);
       ALLOC(e->sa, E + 64); ALLOC(e->rank, E + 64);
@@ -533,7 +536,21 @@ int bz2b200_engine_create(bz2b200_engine** out, int device, int block_size_100k,
    int prev = -1;
    cudaGetDevice(&prev);
    EngineFull* e = nullptr;
-   int rc = engine_new(&e, device, block_size_100k, window_bytes);
+   int rc = engine_new(&e, device, block_size_100k, window_bytes, false);
+   if (prev >= 0) cudaSetDevice(prev);
+   if (rc) return rc;
+   stream_reset(e);
+   *out = reinterpret_cast<bz2b200_engine*>(e);
+   return 0;
+}
+
+int bz2b200_engine_create_bounded(bz2b200_engine** out, int device, int block_size_100k, size_t max_input_bytes)
+{
+   if (!out || max_input_bytes == 0) return set_err(BZ2B200_EPARAM, "bad argument");
+   int prev = -1;
+   cudaGetDevice(&prev);
+   EngineFull* e = nullptr;
+   int rc = engine_new(&e, device, block_size_100k, max_input_bytes, true);
    if (prev >= 0) cudaSetDevice(prev);
    if (rc) return rc;
    stream_reset(e);
@@ -553,6 +570,7 @@ int bz2b200_compress_host(bz2b200_engine* h, const void* src, size_t src_len, vo
 {
    EngineFull* e = reinterpret_cast<EngineFull*>(h);
    if (!e || !dst || !dst_len || (!src && src_len)) return set_err(BZ2B200_EPARAM, "bad argument");
+   if (e->bounded && src_len > e->win_cap) return set_err(BZ2B200_EPARAM, "input larger than this bounded engine was created for");
    DeviceGuard guard(e->device);
    int rc = ensure_staging(e, false);
    if (rc) return rc;
@@ -662,6 +680,7 @@ int bz2b200_stream_begin(bz2b200_engine* h)
 {
    EngineFull* e = reinterpret_cast<EngineFull*>(h);
    if (!e) return set_err(BZ2B200_EPARAM, "null engine");
+   if (e->bounded) return set_err(BZ2B200_EPARAM, "a bounded engine serves one-shot calls only");
    DeviceGuard guard(e->device);
    int rc = ensure_staging(e, true);
    if (rc) return rc;

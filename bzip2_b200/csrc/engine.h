@@ -118,7 +118,8 @@ struct Engine {
    u32 chain_min_round;    // first refinement round that may use chains
    cudaStream_t aux[3];    // side streams of the BWT rounds
    cudaEvent_t ev_fork, ev_join[3];
-   cudaEvent_t ev_s1;         // stage 1: the scalars of the window have reached the host
+   cudaEvent_t ev_s1, ev_s1b; // stage 1: the scalars of the window have reached the host; the stage is complete
+   cudaStream_t s1_stream;    // high-priority stream of stage 1 (set by multi.cu), or null
    u32 *blockmap;          // [enc_cap/4096 + 2] block id of each 4 KiB chunk of enc
    u32 *tie_tmp;           // [blk_cap*256] side buffers of the tie-order replay
    u32 tie_force;          // BZ2_B200_TIE_FORCE=1: replay every exact-power block (tests: closed form == replay)

@@ -40,6 +40,7 @@ struct EngineFull : Engine {
    StreamState ss;
    AsyncFeed af;
    bool debug_keep;
+   bool bounded;               // created for inputs of at most win_cap bytes (one-shot calls): no minimum window
    u32 last_nb, last_E;
    cudaEvent_t ev[6];
    // host path: double-buffered input so the next window's H2D overlaps this window's kernels
@@ -51,7 +52,7 @@ struct EngineFull : Engine {
 };
 
 // engine.cu
-int  engine_new(EngineFull** out, int device, int level, size_t window_bytes);
+int  engine_new(EngineFull** out, int device, int level, size_t window_bytes, bool bounded = false);
 void engine_free(EngineFull* e);
 int  ensure_staging(EngineFull* e, bool need_hin);
 void stream_reset(EngineFull* e);

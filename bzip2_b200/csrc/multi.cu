@@ -224,6 +224,7 @@ static void multi_free(Multi* m)
          if (w.d_shift) cudaFree(w.d_shift);
          if (w.h_seam) cudaFreeHost(w.h_seam);
          if (w.copy_stream) cudaStreamDestroy(w.copy_stream);
+         if (w.e->s1_stream) { cudaStreamDestroy(w.e->s1_stream); w.e->s1_stream = nullptr; }
          if (w.ev_pf) cudaEventDestroy(w.ev_pf);
          engine_free(w.e);
       }
@@ -268,6 +269,11 @@ int bz2b200_multi_create(bz2b200_multi** out, const int* devices, int n_engines,
       ok = ok && cudaMalloc(reinterpret_cast<void**>(&e->d_out), e->out_cap) == cudaSuccess;
       ok = ok && cudaMallocHost(reinterpret_cast<void**>(&w.h_seam), 64) == cudaSuccess;
       ok = ok && cudaStreamCreateWithFlags(&w.copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+      if (ok && !getenv("BZ2_B200_S1_PRIO_OFF")) {
+         int lo = 0, hi = 0;
+         cudaDeviceGetStreamPriorityRange(&lo, &hi);                     // hi is the numerically lowest = highest priority
+         ok = cudaStreamCreateWithPriority(&e->s1_stream, cudaStreamNonBlocking, hi) == cudaSuccess;
+      }
       ok = ok && cudaEventCreateWithFlags(&w.ev_pf, cudaEventDisableTiming) == cudaSuccess;
       if (!ok) { cudaGetLastError(); rc = set_err(BZ2B200_ENOMEM, "device allocation failed (multi-engine staging)"); break; }
       if (pthread_create(&w.th, nullptr, worker_main, &w) != 0) { rc = set_err(BZ2B200_ENOMEM, "cannot start an engine thread"); break; }

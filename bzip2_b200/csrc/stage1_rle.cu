@@ -458,7 +458,14 @@ __global__ void k_s1_consumed(const u32* P, u32* scalars)
 int stage1_run(Engine* e, const u8* d_in, u32 W, bool is_final, bool tail_merge,
                u32* nb_out, u32* consumed_out, u32* enc_total_out)
 {
-   cudaStream_t st = e->stream;
+   // With several engines on one stream of data (multi.cu) the next engine cannot start its window before this
+   // stage has fixed where the window ends, so the stage runs on a high-priority stream when the engine has one:
+   // its CTAs are scheduled ahead of the sorts of the other windows in flight on the same GPU.
+   cudaStream_t st = e->s1_stream ? e->s1_stream : e->stream;
+   if (e->s1_stream) {
+      BZ_CUDA(e, cudaEventRecord(e->ev_s1, e->stream));           // after the window's input copy / output clear
+      BZ_CUDA(e, cudaStreamWaitEvent(st, e->ev_s1, 0));
+   }
    const u32 align = (u32)((uintptr_t)d_in & 15);
    const u32 ntiles = (W + align + S1_TILE - 1) / S1_TILE;
    S1Params p;
@@ -491,6 +498,10 @@ int stage1_run(Engine* e, const u8* d_in, u32 W, bool is_final, bool tail_merge,
    BZ_CUDA(e, cudaMemsetAsync(e->bt.crc, 0, sizeof(u32) * nb_ub, st));
    k_crc<<<dim3(CRC_CTAS_PER_BLOCK, nb_ub), CRC_THREADS, 0, st>>>(d_in, e->bt.P, e->bt.crc, e->s1_scalars); BZ_KCHECK(e);
    k_crc_final<<<(nb_ub + 255) / 256, 256, 0, st>>>(e->bt.crc, e->s1_scalars);            BZ_KCHECK(e);
+   if (e->s1_stream) {
+      BZ_CUDA(e, cudaEventRecord(e->ev_s1b, st));                 // the later stages follow on the engine's stream
+      BZ_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_s1b, 0));
+   }
    BZ_CUDA(e, cudaEventSynchronize(e->ev_s1));
    const u32 nb = e->h_scalars[0];
    *nb_out = nb; *enc_total_out = e->h_scalars[1];

@@ -71,6 +71,9 @@ const char* bz2b200_version(void);
 
 /* window_bytes = 0 picks the default (96 MiB of input per window; at most 100 MiB, at least one block of pure runs). */
 int  bz2b200_engine_create(bz2b200_engine** out, int device, int block_size_100k, size_t window_bytes);
+/* An engine for one-shot calls on inputs of at most max_input_bytes: its window is the input, so a 100 kB call does not
+ * reserve the ~9 GB of HBM a full window needs (the default window must hold a whole block of pure runs: 46 MB at -9). */
+int  bz2b200_engine_create_bounded(bz2b200_engine** out, int device, int block_size_100k, size_t max_input_bytes);
 void bz2b200_engine_destroy(bz2b200_engine* e);
 /* Run on the caller's CUDA stream (a cudaStream_t); NULL restores the engine's own stream. */
 int  bz2b200_engine_set_stream(bz2b200_engine* e, void* cuda_stream);

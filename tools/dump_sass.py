@@ -23,7 +23,7 @@ def main():
         # keep the mnemonic column only: encodings double the size and add nothing for review
         lines = []
         for ln in p.split("\n"):
-            m = re.match(r"\s+/\*([0-9a-f]{4})\*/\s+(.*?)\s*/\*\s*0x[0-9a-f]+\s*\*/", ln)
+            m = re.match(r"\s+/\*([0-9a-f]{4,6})\*/\s+(.*?)\s*/\*\s*0x[0-9a-f]+\s*\*/", ln)
             if m:
                 lines.append(f"/*{m.group(1)}*/ {m.group(2)}")
         open(os.path.join(OUT, short + ".sass"), "w").write(f"// {dem}\n" + "\n".join(lines) + "\n")
