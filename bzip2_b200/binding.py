@@ -66,6 +66,8 @@ def load():
     lib.bz2b200_version.restype = C.c_char_p
     lib.bz2b200_engine_create.restype = C.c_int
     lib.bz2b200_engine_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, sz]
+    lib.bz2b200_engine_create_bounded.restype = C.c_int
+    lib.bz2b200_engine_create_bounded.argtypes = [C.POINTER(vp), C.c_int, C.c_int, sz]
     lib.bz2b200_engine_destroy.restype = None
     lib.bz2b200_engine_destroy.argtypes = [vp]
     lib.bz2b200_engine_set_stream.restype = C.c_int

@@ -269,7 +269,8 @@ int bz2b200_multi_create(bz2b200_multi** out, const int* devices, int n_engines,
       ok = ok && cudaMalloc(reinterpret_cast<void**>(&e->d_out), e->out_cap) == cudaSuccess;
       ok = ok && cudaMallocHost(reinterpret_cast<void**>(&w.h_seam), 64) == cudaSuccess;
       ok = ok && cudaStreamCreateWithFlags(&w.copy_stream, cudaStreamNonBlocking) == cudaSuccess;
-      if (ok && !getenv("BZ2_B200_S1_PRIO_OFF")) {
+      const char* prio_off = getenv("BZ2_B200_S1_PRIO_OFF");
+      if (ok && !(prio_off && *prio_off == '1')) {
          int lo = 0, hi = 0;
          cudaDeviceGetStreamPriorityRange(&lo, &hi);                     // hi is the numerically lowest = highest priority
          ok = cudaStreamCreateWithPriority(&e->s1_stream, cudaStreamNonBlocking, hi) == cudaSuccess;

@@ -420,6 +420,29 @@ def test_custom_allocator_is_used_and_balanced():
     assert not live
 
 
+def test_bounded_engine_for_small_one_shot_calls():
+    """BZ2_bzBuffToBuffCompress sizes the engine to a small input (bz2b200_engine_create_bounded): same bytes as a
+    full-window engine, larger inputs are refused, streaming is refused."""
+    lib = B.load()
+    h = C.c_void_p()
+    assert lib.bz2b200_engine_create_bounded(C.byref(h), 0, 9, 3 << 20) == 0
+    try:
+        d = S.gen_mixed(3_000_000, seg=1 << 17)
+        out = np.empty(4_000_000, np.uint8)
+        n = C.c_size_t(out.size)
+        assert lib.bz2b200_compress_host(h, d.ctypes.data, d.size, out.ctypes.data, C.byref(n), 0, None) == 0
+        assert out[: n.value].tobytes() == S.orc_compress(d, 9)
+        big = S.gen_random(4_000_000)
+        n = C.c_size_t(out.size)
+        assert lib.bz2b200_compress_host(h, big.ctypes.data, big.size, out.ctypes.data, C.byref(n), 0, None) == -1      # BZ2B200_EPARAM
+        assert lib.bz2b200_stream_begin(h) == -1
+    finally:
+        lib.bz2b200_engine_destroy(h)
+    for size in (1, 70_000, 1 << 20, (1 << 20) + 1, 8 << 20, (8 << 20) + 1):       # around the pool's size classes and the 8 MiB limit
+        d = S.gen_text(size, seed=size)
+        assert B.compress(d, 1) == S.orc_compress(d, 1), size
+
+
 def test_outbuff_full():
     lib = B.load()
     d = S.gen_random(50_000)
