@@ -45,6 +45,7 @@ struct MJob {
    u8* dst; size_t cap; unsigned flags; bool pinned;
    pthread_mutex_t mu; pthread_cond_t cv;
    u64 a_w; size_t a_start; bool a_done;            // chain A: window a_w starts at a_start
+   u64 next_ticket;                                  // next window index nobody has taken yet
    u64 b_w; u64 b_bits; u32 b_crc;                   // chain B: window b_w's output starts at bit b_bits
    Seam* seams; size_t n_seams, cap_seams;
    int err; char errtext[256];
@@ -70,7 +71,8 @@ static void job_fail(MJob& J, int rc, const char* text)
 struct HookCtx { MWorker* wk; u64 w; size_t start, W; bool fin; };
 
 // stage 1 of window w has run: hand the start of window w+1 to whoever waits for it, then start copying the input of
-// this engine's next window (w+E) -- its start is not known yet, so copy a region that covers every start it can have
+// the window this engine will most likely take next (w+E: in steady state the engines cycle in order) -- its start is
+// not known yet, so copy a region that covers every start it can have; a wrong guess costs one synchronous copy
 static void multi_after_s1(EngineFull* e, u32 cons, void* vctx)
 {
    HookCtx* c = static_cast<HookCtx*>(vctx);
@@ -100,14 +102,19 @@ static void multi_after_s1(EngineFull* e, u32 cons, void* vctx)
 static int run_job(MWorker* wk)
 {
    Multi* m = wk->m; MJob& J = m->job; EngineFull* e = wk->e;
-   const u64 E = (u64)m->n;
    const bool tail_merge = !(J.flags & BZ2B200_TAIL_STREAMED);
    cudaStream_t st = e->stream;
    stream_reset(e);
    e->ss.header_done = true;
    wk->pf_valid = false;
-   for (u64 w = (u64)wk->idx; ; w += E) {
+   // Window indices are handed out as tickets: engine k starts with window k (so that the first windows spread over the
+   // GPUs in list order), after that a free engine takes the next window nobody has.  Engines that started later in the
+   // chain, or drew the cheaper windows of a mixed input, simply take more of them.
+   bool first = true;
+   for (;;) {
       pthread_mutex_lock(&J.mu);
+      const u64 w = first ? (u64)wk->idx : J.next_ticket++;
+      first = false;
       while (!J.err && !J.a_done && J.a_w < w) pthread_cond_wait(&J.cv, &J.mu);
       if (J.err || J.a_w < w) { pthread_mutex_unlock(&J.mu); break; }     // failed, or the input ended before this window
       const size_t start = J.a_start;
@@ -323,6 +330,7 @@ int bz2b200_multi_compress(bz2b200_multi* h, const void* src, const void* const*
       else cudaGetLastError();
    }
    J.a_w = 0; J.a_start = 0; J.a_done = (n == 0);
+   J.next_ticket = (u64)m->n;
    J.b_w = 0; J.b_bits = 32; J.b_crc = 0;
    J.n_seams = 0; J.err = 0; J.errtext[0] = 0;
    pthread_mutex_lock(&m->mu);
