@@ -23,7 +23,7 @@ namespace bz {
 int concat_bits_stream(u8* d_dst, u64 dst_bit, const u8* d_src, u64 nbits, cudaStream_t st);
 
 constexpr int MAX_ENGINES = 16;
-constexpr size_t PF_SLACK1 = (size_t)2 << 20;        // how far short of a full window a window may stop (run-free data: < 0.9 MB)
+constexpr size_t PF_SLACK1 = (size_t)2 << 20;        // first guess of how far short of a full window a window may stop (run-free data: < 0.9 MB)
 
 struct Multi;
 
@@ -46,6 +46,7 @@ struct MJob {
    pthread_mutex_t mu; pthread_cond_t cv;
    u64 a_w; size_t a_start; bool a_done;            // chain A: window a_w starts at a_start
    u64 next_ticket;                                  // next window index nobody has taken yet
+   size_t max_left; bool left_seen;                  // largest (window size - bytes consumed) seen so far in this job
    u64 b_w; u64 b_bits; u32 b_crc;                   // chain B: window b_w's output starts at bit b_bits
    Seam* seams; size_t n_seams, cap_seams;
    int err; char errtext[256];
@@ -81,12 +82,21 @@ static void multi_after_s1(EngineFull* e, u32 cons, void* vctx)
    J.a_w = c->w + 1;
    J.a_start = c->start + cons;
    if (c->fin || cons == 0) J.a_done = true;
+   if (!c->fin && cons) {
+      const size_t left = c->W - cons;                                     // the window stopped this far short of its end
+      if (!J.left_seen || left > J.max_left) J.max_left = left;
+      J.left_seen = true;
+   }
+   // how far short of a full window the E-1 windows in between may stop: what this job has shown so far plus a margin
+   // (run-free data: < one block), 2 MiB each before anything is known
+   size_t slack1 = J.left_seen ? J.max_left + ((size_t)128 << 10) : PF_SLACK1;
+   if (slack1 > PF_SLACK1 * 4) slack1 = PF_SLACK1 * 4;
    pthread_cond_broadcast(&J.cv);
    pthread_mutex_unlock(&J.mu);
    if (J.dsrc || !J.pinned || c->fin || cons == 0) return;
    const size_t E = (size_t)m->n;
    const size_t next1 = c->start + cons;                                   // start of window w+1
-   const size_t back = (E - 1) * PF_SLACK1;
+   const size_t back = (E - 1) * slack1;
    size_t lo = next1 + (E - 1) * (size_t)e->win_cap;
    lo = (lo > back + next1) ? lo - back : next1;
    if (lo >= J.n) return;
@@ -331,6 +341,7 @@ int bz2b200_multi_compress(bz2b200_multi* h, const void* src, const void* const*
    }
    J.a_w = 0; J.a_start = 0; J.a_done = (n == 0);
    J.next_ticket = (u64)m->n;
+   J.max_left = 0; J.left_seen = false;
    J.b_w = 0; J.b_bits = 32; J.b_crc = 0;
    J.n_seams = 0; J.err = 0; J.errtext[0] = 0;
    pthread_mutex_lock(&m->mu);
