@@ -17,6 +17,7 @@
  * exit status 2 reports corrupt input (bzip2.c:432-553).
  */
 #include "../../include/bzlib.h"
+#include "../../include/bz2_b200.h"
 #include <errno.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -55,9 +56,85 @@ static double now_s(void)
    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 
+/* Regular files of up to 3 GiB are read whole and compressed with ONE call of the engine's one-shot entry point instead
+ * of the reference's read-a-bit / BZ2_bzWrite loop (bzip2.c:350-358): the size is known, so a small file gets an engine
+ * sized to it (no ~9 GB of HBM for a 100 kB file; the engines are kept for the next file of the invocation), and a large
+ * one can be spread over several GPUs / engines (BZ2_B200_DEVICES).  BZ2B200_TAIL_STREAMED keeps the bytes those of the
+ * streaming loop (every input byte arrives in BZ_RUN mode there, bzlib.c:276-308).  BZ2_B200_CLI_STREAM=1 forces the loop. */
+#define ONE_SHOT_MAX ((unsigned long long)3 << 30)
+#define SMALL_FILE   ((size_t)8 << 20)
+static struct { bz2b200_engine* e; int level; size_t cap; } small_eng, big_eng;
+static struct { bz2b200_multi* m; int level; } multi_eng;
+
+static int parse_device_list(const char* v, int* out, int max)
+{
+   int n = 0;
+   while (v && *v && n < max) {
+      char* end;
+      long d = strtol(v, &end, 10);
+      if (end == v) break;
+      out[n++] = (int)d;
+      if (*end != ',') break;
+      v = end + 1;
+   }
+   return n;
+}
+
+static int compress_whole_file(FILE* in, FILE* out, const char* name, size_t size, int lvl,
+                               unsigned long long* nin, unsigned long long* nout)
+{
+   const size_t cap = size + size / 50 + 24576 * (size / (100000 * (size_t)lvl - 19) + 2) + 1024;
+   unsigned char* src = (unsigned char*)malloc(size ? size : 1);
+   unsigned char* dst = (unsigned char*)malloc(cap);
+   size_t dlen = cap, got;
+   int rc, devs[16], ndev;
+   if (!src || !dst) { free(src); free(dst); return -1; }             /* fall back to the streaming loop */
+   got = fread(src, 1, size, in);
+   if (ferror(in)) { fprintf(stderr, "%s: %s: read error: %s\n", prog, name, strerror(errno)); free(src); free(dst); return 1; }
+   if (got != size || fgetc(in) != EOF) { free(src); free(dst); if (fseek(in, 0, SEEK_SET) != 0) return 1; return -1; }   /* the file changed size */
+   ndev = parse_device_list(getenv("BZ2_B200_DEVICES"), devs, 16);
+   if (size <= SMALL_FILE) {
+      size_t want = (size_t)1 << 20;
+      while (want < size) want <<= 1;
+      if (small_eng.e && (small_eng.level != lvl || small_eng.cap < size)) { bz2b200_engine_destroy(small_eng.e); small_eng.e = NULL; }
+      rc = small_eng.e ? 0 : bz2b200_engine_create_bounded(&small_eng.e, getenv("BZ2_B200_DEVICE") ? atoi(getenv("BZ2_B200_DEVICE")) : 0, lvl, want);
+      if (rc == 0) { small_eng.level = lvl; small_eng.cap = want; bz2b200_engine_set_verbosity(small_eng.e, verbose);
+                     rc = bz2b200_compress_host(small_eng.e, src, size, dst, &dlen, BZ2B200_TAIL_STREAMED, NULL); }
+   } else if (ndev >= 2) {
+      if (multi_eng.m && multi_eng.level != lvl) { bz2b200_multi_destroy(multi_eng.m); multi_eng.m = NULL; }
+      rc = multi_eng.m ? 0 : bz2b200_multi_create(&multi_eng.m, devs, ndev, lvl, 0);
+      if (rc == 0) { multi_eng.level = lvl; rc = bz2b200_multi_compress(multi_eng.m, src, NULL, size, dst, &dlen, BZ2B200_TAIL_STREAMED, NULL); }
+   } else {
+      if (big_eng.e && big_eng.level != lvl) { bz2b200_engine_destroy(big_eng.e); big_eng.e = NULL; }
+      rc = big_eng.e ? 0 : bz2b200_engine_create(&big_eng.e, getenv("BZ2_B200_DEVICE") ? atoi(getenv("BZ2_B200_DEVICE")) : 0, lvl, 0);
+      if (rc == 0) { big_eng.level = lvl; bz2b200_engine_set_verbosity(big_eng.e, verbose);
+                     rc = bz2b200_compress_host(big_eng.e, src, size, dst, &dlen, BZ2B200_TAIL_STREAMED, NULL); }
+   }
+   free(src);
+   if (rc) {
+      fprintf(stderr, "%s: %s: the GPU compressor failed (%d: %s)%s\n", prog, name, rc, bz2b200_last_error(),
+              rc == BZ2B200_ENODEV ? "; this build has no CPU path" : "");
+      free(dst);
+      return 1;
+   }
+   if (fwrite(dst, 1, dlen, out) != dlen || fflush(out) != 0) { fprintf(stderr, "%s: write error: %s\n", prog, strerror(errno)); free(dst); return 1; }
+   free(dst);
+   *nin = size; *nout = dlen;
+   return 0;
+}
+
 static int compress_stream(FILE* in, FILE* out, const char* name, unsigned long long* nin, unsigned long long* nout)
 {
    const int timing = getenv("BZ2_B200_CLI_TIMING") != NULL;     /* phase times on stderr */
+   {
+      struct stat sb;
+      const char* force = getenv("BZ2_B200_CLI_STREAM");
+      if (!(force && *force == '1') && fstat(fileno(in), &sb) == 0 && S_ISREG(sb.st_mode) && (unsigned long long)sb.st_size <= ONE_SHOT_MAX
+          && ftell(in) == 0) {
+         const int r = compress_whole_file(in, out, name, (size_t)sb.st_size, small && level > 2 ? 2 : level, nin, nout);
+         if (r >= 0) return r;
+      }
+   }
    double t0 = now_s(), t_open, t_read = 0, t_write = 0, t_loop;
    enum { CHUNK = 4 << 20 };
    int bzerr = BZ_OK;

@@ -105,3 +105,29 @@ def test_level_sweep_reference_decoder(engine_for, tmp_path):
         assert hashlib.sha256(dec.stdout).hexdigest() == want, level
         if S.have_ref():
             assert out == S.ref_compress(d, level), level
+
+
+def test_own_cli_whole_file_paths(tmp_path):
+    """bzip2-b200 reads regular files whole: small files share one input-sized engine, a large file is spread over the
+    engines of BZ2_B200_DEVICES; the bytes are those of the streaming loop (every input byte in BZ_RUN mode)."""
+    cli = os.path.join(os.path.dirname(B.LIB_PATH), "bzip2-b200")
+    ndev = max(1, B.load().bz2b200_device_count())
+    files = {"a.txt": S.gen_text(70_000, seed=1), "b.bin": S.gen_random(2_500_000, seed=9), "c.rec": S.gen_tile(420_000, b"ab\ncd\n."),
+             "empty": np.zeros(0, np.uint8), "big.dat": S.gen_mixed(130_000_000, seg=1 << 22),
+             "edge.dat": (np.arange(99_981 + 1, dtype=np.uint32) % 251).astype(np.uint8)}
+    for name, d in files.items():
+        (tmp_path / name).write_bytes(d.tobytes())
+    env = dict(os.environ, BZ2_B200_DEVICES=",".join(str(i % ndev) for i in range(3)), BZ2_B200_WINDOW_MB="32")
+    r = subprocess.run([cli, "-1", "-k"] + [str(tmp_path / n) for n in files], capture_output=True, env=env)
+    assert r.returncode == 0, r.stderr
+    for name, d in files.items():
+        got = (tmp_path / (name + ".bz2")).read_bytes()
+        if d.size <= 3_000_000:
+            assert got == S.orc_compress(d, 1, tail_merge=0), name
+        else:
+            streamed = subprocess.run([cli, "-1", "-c", str(tmp_path / name)], capture_output=True,
+                                      env=dict(os.environ, BZ2_B200_CLI_STREAM="1"))
+            assert streamed.returncode == 0 and streamed.stdout == got, name
+            dec = subprocess.run([REF_CLI, "-dc", str(tmp_path / (name + ".bz2"))], capture_output=True) if os.path.exists(REF_CLI) else None
+            if dec is not None:
+                assert dec.returncode == 0 and hashlib.sha256(dec.stdout).digest() == hashlib.sha256(d.tobytes()).digest()
