@@ -74,6 +74,27 @@ def test_fails_loudly_without_device(lib):
     with pytest.raises(B.Bz2B200Error):
         B.Engine(level=9)
     assert b"no CUDA device" in lib.bz2b200_last_error()
+    # the multi-engine and input-bounded entry points fail the same way, and so does the one-shot call with a device list
+    with pytest.raises(B.Bz2B200Error):
+        B.Multi([0, 0], level=9)
+    h = C.c_void_p()
+    assert lib.bz2b200_engine_create_bounded(C.byref(h), 0, 9, 1 << 20) == -2        # BZ2B200_ENODEV
+    os.environ["BZ2_B200_DEVICES"] = "0,1"
+    try:
+        n = C.c_uint(dst.size)
+        assert lib.BZ2_bzBuffToBuffCompress(dst.ctypes.data, C.byref(n), src.ctypes.data, 16, 9, 0, 0) == binding.BZ_CONFIG_ERROR
+    finally:
+        del os.environ["BZ2_B200_DEVICES"]
+
+
+def test_multi_param_errors_need_no_gpu(lib):
+    h = C.c_void_p()
+    devs = (C.c_int * 2)(0, 0)
+    assert lib.bz2b200_multi_create(None, devs, 2, 9, 0) == -1                          # BZ2B200_EPARAM
+    assert lib.bz2b200_multi_create(C.byref(h), devs, 0, 9, 0) == -1
+    assert lib.bz2b200_multi_create(C.byref(h), devs, 17, 9, 0) == -1
+    assert lib.bz2b200_multi_engines(None) == 0
+    lib.bz2b200_multi_destroy(None)
 
 
 def test_version_strings(lib):
