@@ -228,13 +228,23 @@ int run_window(EngineFull* e, const u8* d_in, u32 W, bool is_final, bool tail_me
    rc = stage2_run(e, nb, E);
    if (rc) { snprintf(g_err, sizeof g_err, "%s", e->err); return rc; }
    cudaEventRecord(e->ev[2], st);
+   // With several windows in flight on this GPU (multi.cu) the thin, latency-bound stages 3 and 4 also go to the engine's
+   // high-priority stream: their CTAs are scheduled ahead of the register-hungry sort CTAs of the other windows instead
+   // of waiting for a whole grid of them to drain, and the window leaves the GPU sooner.
+   cudaStream_t hp = (e->s1_stream && e->hp_late) ? e->s1_stream : nullptr;
+   if (hp) {
+      BZ_CUDA(e, cudaStreamWaitEvent(hp, e->ev[2], 0));
+      e->stream = hp;
+   }
    rc = stage3_run(e, nb, E);
-   if (rc) { snprintf(g_err, sizeof g_err, "%s", e->err); return rc; }
-   cudaEventRecord(e->ev[3], st);
+   if (rc) { e->stream = st; snprintf(g_err, sizeof g_err, "%s", e->err); return rc; }
+   cudaEventRecord(e->ev[3], e->stream);
    u64 end_bit = 0;
    rc = stage4_run(e, nb, E, d_out, origin_bit, ss.bits, &end_bit);
+   e->stream = st;
    if (rc) { snprintf(g_err, sizeof g_err, "%s", e->err); return rc; }
-   cudaEventRecord(e->ev[4], st);
+   cudaEventRecord(e->ev[4], hp ? hp : st);
+   if (hp) BZ_CUDA(e, cudaStreamWaitEvent(st, e->ev[4], 0));
    // per-block results for the combined CRC and the statistics
    BZ_CUDA(e, cudaMemcpyAsync(e->h_blk, e->bt.crc, sizeof(u32) * nb, cudaMemcpyDeviceToHost, st));
    BZ_CUDA(e, cudaMemcpyAsync(e->h_blk + e->blk_cap, e->bt.nmtf, sizeof(u32) * nb, cudaMemcpyDeviceToHost, st));

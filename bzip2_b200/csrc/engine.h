@@ -120,6 +120,7 @@ struct Engine {
    cudaEvent_t ev_fork, ev_join[3];
    cudaEvent_t ev_s1, ev_s1b; // stage 1: the scalars of the window have reached the host; the stage is complete
    cudaStream_t s1_stream;    // high-priority stream of stage 1 (set by multi.cu), or null
+   u32 hp_late;               // stages 3 and 4 also run on it
    u32 *blockmap;          // [enc_cap/4096 + 2] block id of each 4 KiB chunk of enc
    u32 *tie_tmp;           // [blk_cap*256] side buffers of the tie-order replay
    u32 tie_force;          // BZ2_B200_TIE_FORCE=1: replay every exact-power block (tests: closed form == replay)

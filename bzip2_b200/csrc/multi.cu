@@ -291,6 +291,8 @@ int bz2b200_multi_create(bz2b200_multi** out, const int* devices, int n_engines,
          int lo = 0, hi = 0;
          cudaDeviceGetStreamPriorityRange(&lo, &hi);                     // hi is the numerically lowest = highest priority
          ok = cudaStreamCreateWithPriority(&e->s1_stream, cudaStreamNonBlocking, hi) == cudaSuccess;
+         const char* late = getenv("BZ2_B200_HP_LATE");
+         e->hp_late = (late && *late == '0') ? 0u : 1u;
       }
       ok = ok && cudaEventCreateWithFlags(&w.ev_pf, cudaEventDisableTiming) == cudaSuccess;
       if (!ok) { cudaGetLastError(); rc = set_err(BZ2B200_ENOMEM, "device allocation failed (multi-engine staging)"); break; }
