@@ -35,7 +35,7 @@ struct MWorker {
    pthread_t th; bool started;
    u64 seen_seq;
    u8* dbuf[2]; size_t dcap; int cur;               // device input staging (host sources)
-   size_t pf_lo, pf_len; bool pf_valid;
+   size_t pf_lo, pf_hi, pf_core_b, pf_core_e; bool pf_valid;   // prefetch: start range of the next window, the bytes already copied
    cudaStream_t copy_stream; cudaEvent_t ev_pf;
    u8* d_shift; u8* h_seam;                          // shifted output; pinned scratch for the seam bytes
 };
@@ -43,6 +43,7 @@ struct MWorker {
 struct MJob {
    const u8* src; const u8* const* dsrc; size_t n;
    u8* dst; size_t cap; unsigned flags; bool pinned;
+   bool prefetching;                                 // pinned host source: fixed window order, input copied ahead
    pthread_mutex_t mu; pthread_cond_t cv;
    u64 a_w; size_t a_start; bool a_done;            // chain A: window a_w starts at a_start
    u64 next_ticket;                                  // next window index nobody has taken yet
@@ -72,8 +73,11 @@ static void job_fail(MJob& J, int rc, const char* text)
 struct HookCtx { MWorker* wk; u64 w; size_t start, W; bool fin; };
 
 // stage 1 of window w has run: hand the start of window w+1 to whoever waits for it, then start copying the input of
-// the window this engine will most likely take next (w+E: in steady state the engines cycle in order) -- its start is
-// not known yet, so copy a region that covers every start it can have; a wrong guess costs one synchronous copy
+// this engine's next window.  With a pinned host source the engines take the windows in a fixed cycle (engine k: windows
+// k, k+E, ...), so the next one is w+E; its start is known only up to how far the E-1 windows in between stop short of
+// full size.  Every start in [lo, hi] needs the bytes [hi, lo + window) -- that CORE is copied now, behind the sort;
+// the edges on either side (at most hi - lo bytes, ~1 MB per engine in between on run-free data) are copied when the
+// window starts.  Nothing is copied twice, and only the edges sit in front of stage 1.
 static void multi_after_s1(EngineFull* e, u32 cons, void* vctx)
 {
    HookCtx* c = static_cast<HookCtx*>(vctx);
@@ -90,23 +94,27 @@ static void multi_after_s1(EngineFull* e, u32 cons, void* vctx)
    // how far short of a full window the E-1 windows in between may stop: what this job has shown so far plus a margin
    // (run-free data: < one block), 2 MiB each before anything is known
    size_t slack1 = J.left_seen ? J.max_left + ((size_t)128 << 10) : PF_SLACK1;
-   if (slack1 > PF_SLACK1 * 4) slack1 = PF_SLACK1 * 4;
+   if (slack1 > PF_SLACK1) slack1 = PF_SLACK1;                            // the staging buffers are sized for this
    pthread_cond_broadcast(&J.cv);
    pthread_mutex_unlock(&J.mu);
-   if (J.dsrc || !J.pinned || c->fin || cons == 0) return;
-   const size_t E = (size_t)m->n;
+   if (!J.prefetching || c->fin || cons == 0) return;
+   const size_t E = (size_t)m->n, Wc = (size_t)e->win_cap;
    const size_t next1 = c->start + cons;                                   // start of window w+1
-   const size_t back = (E - 1) * slack1;
-   size_t lo = next1 + (E - 1) * (size_t)e->win_cap;
-   lo = (lo > back + next1) ? lo - back : next1;
+   const size_t hi = next1 + (E - 1) * Wc;                                 // latest and earliest start of window w+E
+   const size_t lo = hi - (E - 1) * slack1;
    if (lo >= J.n) return;
-   size_t len = (size_t)e->win_cap + back;
-   if (len > J.n - lo) len = J.n - lo;
-   if (len > wk->dcap) len = wk->dcap;
+   const size_t core_b = hi < J.n ? hi : J.n;
+   const size_t core_e = (lo + Wc < J.n) ? lo + Wc : J.n;
    const int nb = wk->cur ^ 1;
-   if (cudaMemcpyAsync(wk->dbuf[nb], J.src + lo, len, cudaMemcpyHostToDevice, wk->copy_stream) != cudaSuccess) { cudaGetLastError(); return; }
+   wk->pf_lo = lo; wk->pf_hi = hi; wk->pf_core_b = core_b; wk->pf_core_e = core_e > core_b ? core_e : core_b;
+   if (core_e > core_b) {
+      if (cudaMemcpyAsync(wk->dbuf[nb] + (core_b - lo), J.src + core_b, core_e - core_b, cudaMemcpyHostToDevice, wk->copy_stream) != cudaSuccess) {
+         cudaGetLastError();
+         return;
+      }
+   }
    cudaEventRecord(wk->ev_pf, wk->copy_stream);
-   wk->pf_lo = lo; wk->pf_len = len; wk->pf_valid = true;
+   wk->pf_valid = true;
 }
 
 static int run_job(MWorker* wk)
@@ -117,14 +125,17 @@ static int run_job(MWorker* wk)
    stream_reset(e);
    e->ss.header_done = true;
    wk->pf_valid = false;
-   // Window indices are handed out as tickets: engine k starts with window k (so that the first windows spread over the
-   // GPUs in list order), after that a free engine takes the next window nobody has.  Engines that started later in the
-   // chain, or drew the cheaper windows of a mixed input, simply take more of them.
+   // Which engine takes which window.  With a pinned host source the order is a fixed cycle (engine k: windows k, k+E,
+   // ...), which is what lets an engine copy its next window's input ahead of time.  Otherwise (resident input, or a
+   // pageable source that cannot be copied asynchronously anyway) window indices are tickets: engine k starts with
+   // window k, after that a free engine takes the next window nobody has, so engines that started later in the chain,
+   // or drew the cheaper windows of a mixed input, simply take more of them.
    bool first = true;
+   u64 wprev = 0;
    for (;;) {
       pthread_mutex_lock(&J.mu);
-      const u64 w = first ? (u64)wk->idx : J.next_ticket++;
-      first = false;
+      const u64 w = first ? (u64)wk->idx : (J.prefetching ? wprev + (u64)m->n : J.next_ticket++);
+      first = false; wprev = w;
       while (!J.err && !J.a_done && J.a_w < w) pthread_cond_wait(&J.cv, &J.mu);
       if (J.err || J.a_w < w) { pthread_mutex_unlock(&J.mu); break; }     // failed, or the input ended before this window
       const size_t start = J.a_start;
@@ -134,10 +145,17 @@ static int run_job(MWorker* wk)
       const bool fin = (start + W == J.n);
       const u8* d_in;
       if (J.dsrc) d_in = J.dsrc[wk->idx] + start;
-      else if (wk->pf_valid && start >= wk->pf_lo && start + W <= wk->pf_lo + wk->pf_len) {
+      else if (wk->pf_valid && start >= wk->pf_lo && start <= wk->pf_hi && (start - wk->pf_lo) + W <= wk->dcap) {
+         // the core is there (or on its way); fetch the edges this start needs
          wk->cur ^= 1;
+         u8* buf = wk->dbuf[wk->cur];
          BZ_CUDA(e, cudaStreamWaitEvent(st, wk->ev_pf, 0));
-         d_in = wk->dbuf[wk->cur] + (start - wk->pf_lo);
+         const size_t end = start + W;
+         const size_t head_e = wk->pf_core_b < end ? wk->pf_core_b : end;
+         if (start < head_e) BZ_CUDA(e, cudaMemcpyAsync(buf + (start - wk->pf_lo), J.src + start, head_e - start, cudaMemcpyHostToDevice, st));
+         const size_t tail_b = wk->pf_core_e > start ? wk->pf_core_e : start;
+         if (tail_b < end && wk->pf_core_e > wk->pf_core_b) BZ_CUDA(e, cudaMemcpyAsync(buf + (tail_b - wk->pf_lo), J.src + tail_b, end - tail_b, cudaMemcpyHostToDevice, st));
+         d_in = buf + (start - wk->pf_lo);
       } else {
          if (wk->pf_valid) BZ_CUDA(e, cudaStreamSynchronize(wk->copy_stream));                      // a guess that missed
          BZ_CUDA(e, cudaMemcpyAsync(wk->dbuf[wk->cur], J.src + start, W, cudaMemcpyHostToDevice, st));
@@ -341,6 +359,7 @@ int bz2b200_multi_compress(bz2b200_multi* h, const void* src, const void* const*
       if (cudaPointerGetAttributes(&at, src) == cudaSuccess) J.pinned = (at.type == cudaMemoryTypeHost);
       else cudaGetLastError();
    }
+   J.prefetching = J.pinned && !J.dsrc;
    J.a_w = 0; J.a_start = 0; J.a_done = (n == 0);
    J.next_ticket = (u64)m->n;
    J.max_left = 0; J.left_seen = false;
