@@ -17,6 +17,7 @@
 #include "engine_full.h"
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 namespace bz {
 
@@ -62,6 +63,22 @@ struct Multi {
    pthread_mutex_t call_mu;                          // one job at a time
 };
 
+static double now_s()
+{
+   struct timespec ts;
+   clock_gettime(CLOCK_MONOTONIC, &ts);
+   return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+static inline void cpu_relax()
+{
+#if defined(__x86_64__) || defined(__i386__)
+   __builtin_ia32_pause();
+#else
+   __asm__ __volatile__("" ::: "memory");
+#endif
+}
+
 static void job_fail(MJob& J, int rc, const char* text)
 {
    pthread_mutex_lock(&J.mu);
@@ -70,7 +87,7 @@ static void job_fail(MJob& J, int rc, const char* text)
    pthread_mutex_unlock(&J.mu);
 }
 
-struct HookCtx { MWorker* wk; u64 w; size_t start, W; bool fin; };
+struct HookCtx { MWorker* wk; u64 w; size_t start, W; bool fin; double t0; double* t_s1; };
 
 // stage 1 of window w has run: hand the start of window w+1 to whoever waits for it, then start copying the input of
 // this engine's next window.  With a pinned host source the engines take the windows in a fixed cycle (engine k: windows
@@ -82,6 +99,7 @@ static void multi_after_s1(EngineFull* e, u32 cons, void* vctx)
 {
    HookCtx* c = static_cast<HookCtx*>(vctx);
    MWorker* wk = c->wk; Multi* m = wk->m; MJob& J = m->job;
+   *c->t_s1 += now_s() - c->t0;
    pthread_mutex_lock(&J.mu);
    J.a_w = c->w + 1;
    J.a_start = c->start + cons;
@@ -125,6 +143,11 @@ static int run_job(MWorker* wk)
    stream_reset(e);
    e->ss.header_done = true;
    wk->pf_valid = false;
+   // the output buffer is cleared here and again as soon as a window's output has left it -- not in front of stage 1 of
+   // the next window, where the clear would sit on the chain every other engine waits for
+   BZ_CUDA(e, cudaMemsetAsync(e->d_out, 0, e->out_cap, st));
+   double t_wait_a = 0, t_wait_b = 0, t_s1 = 0, t_job0 = now_s();
+   u32 n_win = 0;
    // Which engine takes which window.  With a pinned host source the order is a fixed cycle (engine k: windows k, k+E,
    // ...), which is what lets an engine copy its next window's input ahead of time.  Otherwise (resident input, or a
    // pageable source that cannot be copied asynchronously anyway) window indices are tickets: engine k starts with
@@ -136,7 +159,15 @@ static int run_job(MWorker* wk)
       pthread_mutex_lock(&J.mu);
       const u64 w = first ? (u64)wk->idx : (J.prefetching ? wprev + (u64)m->n : J.next_ticket++);
       first = false; wprev = w;
-      while (!J.err && !J.a_done && J.a_w < w) pthread_cond_wait(&J.cv, &J.mu);
+      const double tw0 = now_s();
+      while (!J.err && !J.a_done && J.a_w < w) {
+         if (J.a_w + 1 == w) {                                            // next in line: poll instead of sleeping
+            pthread_mutex_unlock(&J.mu);
+            for (int k = 0; k < 64; k++) cpu_relax();
+            pthread_mutex_lock(&J.mu);
+         } else pthread_cond_wait(&J.cv, &J.mu);
+      }
+      t_wait_a += now_s() - tw0;
       if (J.err || J.a_w < w) { pthread_mutex_unlock(&J.mu); break; }     // failed, or the input ended before this window
       const size_t start = J.a_start;
       pthread_mutex_unlock(&J.mu);
@@ -162,9 +193,9 @@ static int run_job(MWorker* wk)
          d_in = wk->dbuf[wk->cur];
       }
       wk->pf_valid = false;
-      HookCtx ctx = { wk, w, start, W, fin };
+      HookCtx ctx = { wk, w, start, W, fin, now_s(), &t_s1 };
+      n_win++;
       e->after_s1 = multi_after_s1; e->after_s1_ctx = &ctx;
-      BZ_CUDA(e, cudaMemsetAsync(e->d_out, 0, e->out_cap, st));
       e->ss.bits = 0; e->ss.combined_crc = 0;
       const u32 blocks_before = e->ss.block_no;
       u32 cons = 0, nb = 0;
@@ -177,7 +208,9 @@ static int run_job(MWorker* wk)
       const u32 fold_w = e->ss.combined_crc;
       // chain B: my output starts where the previous window's ended
       pthread_mutex_lock(&J.mu);
+      const double tb0 = now_s();
       while (!J.err && J.b_w < w) pthread_cond_wait(&J.cv, &J.mu);
+      t_wait_b += now_s() - tb0;
       if (J.err) { pthread_mutex_unlock(&J.mu); break; }
       const u64 B = J.b_bits;
       const u32 r32 = nb & 31u;
@@ -209,6 +242,7 @@ static int run_job(MWorker* wk)
       if (i1 > i0) BZ_CUDA(e, cudaMemcpyAsync(J.dst + (B >> 3) + i0, srcbuf + i0, i1 - i0, cudaMemcpyDeviceToHost, st));
       BZ_CUDA(e, cudaMemcpyAsync(wk->h_seam, srcbuf, 1, cudaMemcpyDeviceToHost, st));
       BZ_CUDA(e, cudaMemcpyAsync(wk->h_seam + 8, srcbuf + i1, 1, cudaMemcpyDeviceToHost, st));
+      BZ_CUDA(e, cudaMemsetAsync(e->d_out, 0, e->out_cap, st));           // for this engine's next window
       BZ_CUDA(e, cudaStreamSynchronize(st));
       pthread_mutex_lock(&J.mu);
       Seam& s = J.seams[w];
@@ -217,6 +251,14 @@ static int run_job(MWorker* wk)
       s.tail = (endrel & 7) ? wk->h_seam[8] : 0;
       pthread_mutex_unlock(&J.mu);
       if (fin) break;
+   }
+   {
+      // BZ2_B200_MULTI_TRACE=1: where this engine's time went (waiting for its window's start / for its output offset,
+      // stage 1 incl. its host round trip, everything else)
+      static int trace = -1;
+      if (trace < 0) { const char* v = getenv("BZ2_B200_MULTI_TRACE"); trace = (v && *v == '1') ? 1 : 0; }
+      if (trace) fprintf(stderr, "[bz2b200 multi] engine %2d (gpu %d): %u windows, %.1f ms total, wait start %.1f, stage 1 %.1f, wait offset %.1f\n",
+                         wk->idx, e->device, n_win, (now_s() - t_job0) * 1e3, t_wait_a * 1e3, t_s1 * 1e3, t_wait_b * 1e3);
    }
    return 0;
 }
