@@ -128,6 +128,7 @@ int engine_new(EngineFull** out, int device, int level, size_t window_bytes, boo
       c0 = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
       if (c0 == cudaSuccess) c0 = cudaEventCreateWithFlags(&e->ev_s1, cudaEventDisableTiming);
       if (c0 == cudaSuccess) c0 = cudaEventCreateWithFlags(&e->ev_s1b, cudaEventDisableTiming);
+      if (c0 == cudaSuccess) c0 = cudaEventCreateWithFlags(&e->ev_fast, cudaEventDisableTiming);
       if (c0 != cudaSuccess) { rc = engine_fail(e, c0, __FILE__, __LINE__); goto fail; }
       ALLOC(e->enc, E + 64); ALLOC(e->cend, E + 64);
       ALLOC(e->sa, E + 64); ALLOC(e->rank, E + 64);
@@ -211,6 +212,12 @@ void stream_reset(EngineFull* e)
 
 // One window through all stages.  d_in: device input; writes coded blocks into d_out at
 // their absolute bit positions (relative to origin_bit) and advances ss.bits.
+static void s1_early_trampoline(Engine* b, u32 consumed)
+{
+   EngineFull* f = static_cast<EngineFull*>(b);
+   f->after_s1(f, consumed, f->after_s1_ctx);
+}
+
 int run_window(EngineFull* e, const u8* d_in, u32 W, bool is_final, bool tail_merge,
                       u8* d_out, u64 origin_bit, u32* consumed, u32* nb_out)
 {
@@ -218,10 +225,14 @@ int run_window(EngineFull* e, const u8* d_in, u32 W, bool is_final, bool tail_me
    u32 nb = 0, cons = 0, E = 0;
    StreamState& ss = e->ss;
    cudaEventRecord(e->ev[0], st);
+   // several engines on one stream of data: stage 1 may hand the window's end to the next engine before it is done
+   e->s1_early_done = false;
+   e->s1_early = (e->after_s1 && e->s1_stream) ? s1_early_trampoline : nullptr;
    int rc = stage1_run(e, d_in, W, is_final, tail_merge, &nb, &cons, &E);
+   e->s1_early = nullptr;
    if (rc) { snprintf(g_err, sizeof g_err, "%s", e->err); return rc; }
    cudaEventRecord(e->ev[1], st);
-   if (e->after_s1) e->after_s1(e, cons, e->after_s1_ctx);
+   if (e->after_s1 && !e->s1_early_done) e->after_s1(e, cons, e->after_s1_ctx);
    *consumed = cons; *nb_out = nb;
    e->last_nb = nb; e->last_E = E;
    if (nb == 0) return 0;

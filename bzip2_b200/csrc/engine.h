@@ -121,6 +121,10 @@ struct Engine {
    cudaEvent_t ev_s1, ev_s1b; // stage 1: the scalars of the window have reached the host; the stage is complete
    cudaStream_t s1_stream;    // high-priority stream of stage 1 (set by multi.cu), or null
    u32 hp_late;               // stages 3 and 4 also run on it
+   // stage 1 may report the window's consumed bytes before it has finished (fast split of run-free windows, stage1_rle.cu)
+   void (*s1_early)(Engine*, u32 consumed);
+   bool s1_early_done;
+   cudaEvent_t ev_fast;
    u32 *blockmap;          // [enc_cap/4096 + 2] block id of each 4 KiB chunk of enc
    u32 *tie_tmp;           // [blk_cap*256] side buffers of the tie-order replay
    u32 tie_force;          // BZ2_B200_TIE_FORCE=1: replay every exact-power block (tests: closed form == replay)

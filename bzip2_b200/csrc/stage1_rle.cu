@@ -455,6 +455,50 @@ __global__ void k_s1_consumed(const u32* P, u32* scalars)
    scalars[3] = nb ? P[nb] : 0;
 }
 
+// ---- fast split of run-free windows ----------------------------------------------------------------
+// When several engines work on one stream of data, the next engine can start only when this window's end -- its last
+// block boundary -- is known; at eight GPUs that hand-over is the critical path of the whole job (one per 100 MB).
+// For a window without any run of four or more equal bytes the RLE1 output IS the input, a chunk ends wherever the
+// next byte differs, and the boundary chain of k_chain can be walked on the raw input long before the tiles have been
+// scanned, counted and scattered: one streaming test (k_has_run4), one warp (k_chain_raw).  The result is checked
+// against the full computation afterwards; windows with longer runs take the normal path.
+__global__ void __launch_bounds__(256) k_has_run4(const u8* in, u32 W, u32* flag)
+{
+   const u64 q0 = ((u64)blockIdx.x * 256 + threadIdx.x) * 16;
+   // bytes q0-3 .. q0+15: a run of four ends at q iff in[q-3..q] are equal
+   u32 run = 1;
+   bool hit = false;
+   u32 prev = (q0 >= 3 && q0 - 3 < W) ? in[q0 - 3] : 256u;
+   for (int k = -2; k < 16 && q0 < W; k++) {
+      const i64 q = (i64)q0 + k;
+      if (q < 0 || q >= (i64)W) { prev = 256u; run = 1; continue; }
+      const u32 c = in[q];
+      run = (c == prev) ? run + 1 : 1;
+      prev = c;
+      if (run >= 4) hit = true;
+   }
+   if (__any_sync(FULL, hit) && lane_id() == 0) atomicOr(flag, 1u);
+}
+
+// k_chain on the raw input of a NON-FINAL window without runs of four: out[0] = flag, out[1] = consumed, out[2] = blocks
+__global__ void k_chain_raw(const u8* in, u32 W, u32 nmax, u32 blk_cap, const u32* flag, u32* out)
+{
+   const u32 l = lane_id();
+   if (*flag) { if (l == 0) { out[0] = 1; out[1] = 0; out[2] = 0; } return; }
+   u32 x = 0, nb = 0;
+   while (x < W && nb < blk_cap) {
+      const u32 target = x + nmax - 1;
+      if (target >= W) break;
+      const u32 e = target + l;
+      const bool f = (l < 8) && (e + 1 < W) && (in[e + 1] != in[e]);      // a chunk ends where the next byte differs
+      const u32 m = __ballot_sync(FULL, f);
+      if (m == 0) break;
+      x = target + (u32)(__ffs(m) - 1) + 1;
+      nb++;
+   }
+   if (l == 0) { out[0] = 0; out[1] = x; out[2] = nb; }
+}
+
 int stage1_run(Engine* e, const u8* d_in, u32 W, bool is_final, bool tail_merge,
                u32* nb_out, u32* consumed_out, u32* enc_total_out)
 {
@@ -482,6 +526,14 @@ int stage1_run(Engine* e, const u8* d_in, u32 W, bool is_final, bool tail_merge,
    if (nb_ub > e->blk_cap) nb_ub = e->blk_cap;
    if (Eub > e->enc_cap) { snprintf(e->err, sizeof e->err, "window %u too large for the engine (capacity %u)", W, e->win_cap); return -3; }
    p.nb_find = 1;
+   const bool fast = e->s1_early && !is_final && W > 4u * e->nmax;
+   if (fast) {
+      BZ_CUDA(e, cudaMemsetAsync(e->s1_scalars + 8, 0, 4 * sizeof(u32), st));
+      k_has_run4<<<(W / 16 + 256) / 256, 256, 0, st>>>(d_in, W, e->s1_scalars + 8);        BZ_KCHECK(e);
+      k_chain_raw<<<1, 32, 0, st>>>(d_in, W, e->nmax, e->blk_cap, e->s1_scalars + 8, e->s1_scalars + 9); BZ_KCHECK(e);
+      BZ_CUDA(e, cudaMemcpyAsync(e->h_scalars + 16, e->s1_scalars + 9, 3 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+      BZ_CUDA(e, cudaEventRecord(e->ev_fast, st));
+   }
    k_tile<S1_AGG><<<ntiles, S1_THREADS, 0, st>>>(p);                                   BZ_KCHECK(e);
    k_scan_runs<<<1, 1024, 0, st>>>(e->tile_len, e->tile_ext, e->tile_carry, ntiles, 0);   BZ_KCHECK(e);
    k_tile<S1_COUNT><<<ntiles, S1_THREADS, 0, st>>>(p);                                 BZ_KCHECK(e);
@@ -502,7 +554,20 @@ int stage1_run(Engine* e, const u8* d_in, u32 W, bool is_final, bool tail_merge,
       BZ_CUDA(e, cudaEventRecord(e->ev_s1b, st));                 // the later stages follow on the engine's stream
       BZ_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_s1b, 0));
    }
+   u32 fast_cons = 0;
+   if (fast) {
+      BZ_CUDA(e, cudaEventSynchronize(e->ev_fast));
+      if (e->h_scalars[16] == 0 && e->h_scalars[17] != 0) {
+         fast_cons = e->h_scalars[17];
+         e->s1_early(e, fast_cons);                          // the next engine starts its window now
+         e->s1_early_done = true;
+      }
+   }
    BZ_CUDA(e, cudaEventSynchronize(e->ev_s1));
+   if (fast_cons && (e->h_scalars[0] == 0 || e->h_scalars[3] != fast_cons)) {
+      snprintf(e->err, sizeof e->err, "fast block split disagrees with the full one (%u vs %u)", fast_cons, e->h_scalars[3]);
+      return -6;
+   }
    const u32 nb = e->h_scalars[0];
    *nb_out = nb; *enc_total_out = e->h_scalars[1];
    *consumed_out = nb ? e->h_scalars[3] : 0;
