@@ -398,7 +398,9 @@ int BZ2_bzDecompress(bz_stream* strm)
          uint64_t at = 0;
          found = find_next_magic(s, &at);
          if (!found) {
-            if ((uint64_t)s->ilen > (uint64_t)s->level * 130000 + 100000) { s->phase = D_ERROR; return s->err = BZ_DATA_ERROR; }
+            /* a legal block of a foreign encoder may spend up to 20 bits on every symbol (the format's code-length limit):
+             * 2.5 bytes per block byte plus selectors and tables */
+            if ((uint64_t)s->ilen > (uint64_t)s->level * 250000 + 100000) { s->phase = D_ERROR; return s->err = BZ_DATA_ERROR; }
             if (!take_byte(s)) return s->phase == D_ERROR ? s->err : BZ_OK;
             continue;
          }
