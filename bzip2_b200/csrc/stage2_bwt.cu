@@ -1432,7 +1432,7 @@ int stage2_run(Engine* e, u32 nb, u32 E)
    p.hist = e->hist; p.hist_stride = e->hist_stride; p.code = e->code; p.kk = e->kk; p.nbins = e->nbins;
    p.hh = e->hh; p.kbits = e->kbits; p.ksym = e->ksym; p.K = e->K; p.kscrA = e->kscrA; p.kscrB = e->kscrB;
    p.debug = trace_on() ? 1 : 0;
-   { static int agg = -1; if (agg < 0) { const char* v = getenv("BZ2_B200_KG_AGG"); agg = v ? atoi(v) : (int)KG_AGG_MAX_ALPHA; } p.kg_agg_alpha = (u32)agg; }
+   p.kg_agg_alpha = KG_AGG_MAX_ALPHA;
    p.blockmap = e->blockmap;
    p.power_q = e->bt.power_q; p.inuse = e->bt.inuse; p.ninuse = e->bt.ninuse;
    p.jd = nullptr; p.jq = nullptr; p.dstar = nullptr;
@@ -1455,9 +1455,7 @@ int stage2_run(Engine* e, u32 nb, u32 E)
       k_codemap<<<g, 256, 0, st>>>(p);                                                          BZ_KCHECK(e);
       // one atomic pass: the count pass keeps each rotation's arrival index inside its bucket, so the
       // placement pass needs no atomics (bucket start + arrival index)
-      if (p.kg_agg_alpha) k_kgram<KG_HISTOFF, true><<<gtiles, KG_THREADS, 0, st>>>(p);
-      else                k_kgram<KG_HISTOFF, false><<<gtiles, KG_THREADS, 0, st>>>(p);
-      BZ_KCHECK(e);
+      k_kgram<KG_HISTOFF, true><<<gtiles, KG_THREADS, 0, st>>>(p);                              BZ_KCHECK(e);
       k_kgram_scan<<<g, 1024, 0, st>>>(p);                                                      BZ_KCHECK(e);
       k_kgram<KG_PLACE, false><<<gtiles, KG_THREADS, 0, st>>>(p);                                      BZ_KCHECK(e);
       k_seg_init<<<dim3((e->hist_stride + 255) / 256, g), 256, 0, st>>>(p, lists_dev(e, 0));    BZ_KCHECK(e);

@@ -319,70 +319,6 @@ __global__ void __launch_bounds__(MTF_CTA) k_mtf_encode(S3Params p)
 }
 
 
-// Warp-cooperative variant for high-entropy blocks (mean MTF position large): the list lives in
-// registers, 8 bytes per lane; a symbol is located with a SWAR zero-byte test and a ballot and
-// rotated to the front with one shuffle.  Cost per symbol does not depend on its position.
-__global__ void __launch_bounds__(256) k_mtf_encode_warp(S3Params p)
-{
-   const u32 w = threadIdx.x >> 5, l = lane_id();
-   const u32 b = blockIdx.y;
-   if (!p.mode[b]) return;
-   const u32 t = blockIdx.x * 8 + w;
-   const u32 xb = p.X[b], n = p.X[b + 1] - xb;
-   if ((u64)t * MTF_TILE >= n) return;
-   const u32 start = xb + t * MTF_TILE;
-   const u32 size = min((u32)MTF_TILE, n - t * MTF_TILE);
-   u64 L = reinterpret_cast<const u64*>(p.lists + ((size_t)b * p.tiles_max + t) * 256)[l];
-   u32 front = __shfl_sync(FULL, (u32)(L & 0xff), 0);
-   u32 lead = 0, run = 0, inner = 0;
-   bool seen_nz = false;
-   for (u32 base = 0; base < size; base += 32) {
-      const u32 i = base + l;
-      const u32 sym = (i < size) ? p.bwt[start + i] : 0;
-      const u32 cntj = min(32u, size - base);
-      u32 myz = 0;
-      for (u32 j = 0; j < cntj; j++) {
-         const u32 c = __shfl_sync(FULL, sym, j);
-         u32 pos = 0;
-         if (c != front) {
-            const u64 x = L ^ (0x0101010101010101ULL * (u64)c);
-            const u64 zm = (x - 0x0101010101010101ULL) & ~x & 0x8080808080808080ULL;
-            const u32 hit = __ballot_sync(FULL, zm != 0);
-            if (hit) {
-               const u32 f = __ffs(hit) - 1;
-               u32 bi = zm ? (u32)((__ffsll((long long)zm) - 1) >> 3) : 0;
-               bi = __shfl_sync(FULL, bi, f);
-               pos = f * 8 + bi;
-               u32 top = __shfl_up_sync(FULL, (u32)(L >> 56), 1);
-               if (l == 0) top = c;
-               if (l < f) L = (L << 8) | (u64)top;
-               else if (l == f) {
-                  const u64 lowmask = bi ? ((1ULL << (8 * bi)) - 1ULL) : 0ULL;
-                  const u64 keepmask = (bi == 7) ? 0ULL : ~((1ULL << (8 * (bi + 1))) - 1ULL);
-                  L = (L & keepmask) | ((L & lowmask) << 8) | (u64)top;
-               }
-               front = c;
-            }
-         }
-         if (l == j) myz = pos;
-         // zero-run shape (uniform across the warp)
-         if (pos == 0) run++;
-         else {
-            if (!seen_nz) { lead = run; seen_nz = true; }
-            else if (run) inner += run_digits(run);
-            inner += 1;
-            run = 0;
-         }
-      }
-      if (i < size) p.z[start + i] = (u8)myz;
-   }
-   if (l == 0) {
-      u32* m = p.tmeta + ((size_t)b * p.tiles_max + t) * 4;
-      if (!seen_nz) { m[0] = size; m[1] = size | 0x80000000u; m[2] = 0; }
-      else { m[0] = lead; m[1] = run; m[2] = inner; }
-   }
-}
-
 // Zero-run stitching across tiles: one WARP per block.  A range of tiles is summarised as
 // (all-zero?, leading zeros, trailing zeros, symbols emitted after the leading run), which
 // composes associatively, so the carry into every tile is an exclusive scan.
@@ -542,9 +478,9 @@ int stage3_run(Engine* e, u32 nb, u32 E)
    S3Params p;
    p.bwt = e->bwt; p.X = e->bt.X; p.inuse = e->bt.inuse; p.ninuse = e->bt.ninuse;
    p.lists = e->mtf_summary; p.tilecnt = e->mtf_tilecnt; p.mode = e->mtf_mode;
-   // measured on B200: the thread-per-tile kernel wins even on uniform random bytes (120 vs 137 ms/GB),
-   // so the warp variant is off unless BZ2_B200_MTF_WARP sets a threshold (<= 256)
-   { const char* v = getenv("BZ2_B200_MTF_WARP"); p.warp_threshold = v ? (u32)atoi(v) : 1000u; } p.tmeta = e->mtf_tilemeta;
+   // (a warp-cooperative encoder for high-entropy blocks was measured in round 1: the thread-per-tile kernel wins even on
+   // uniform random bytes, 120 vs 137 ms/GB; it is no longer in the tree and no block is ever marked for it)
+   p.warp_threshold = 1000u; p.tmeta = e->mtf_tilemeta;
    p.tcarry = e->mtf_tilemeta + (size_t)e->blk_cap * tiles_max * 4;
    p.z = e->z; p.mtfv = e->mtfv; p.nmtf = e->bt.nmtf; p.mtffreq = e->bt.mtffreq; p.tiles_max = tiles_max;
    BZ_CUDA(e, cudaMemsetAsync(e->bt.mtffreq, 0, sizeof(i32) * BZ_MAX_ALPHA * nb, st));
@@ -553,7 +489,6 @@ int stage3_run(Engine* e, u32 nb, u32 E)
    k_mtf_summary<<<gw, 256, 0, st>>>(p);                BZ_KCHECK(e);
    k_mtf_lists<<<(nb + ML_WARPS - 1) / ML_WARPS, ML_WARPS * 32, 0, st>>>(p, nb);   BZ_KCHECK(e);
    k_mtf_encode<<<gt, MTF_CTA, 0, st>>>(p);             BZ_KCHECK(e);
-   k_mtf_encode_warp<<<gw, 256, 0, st>>>(p);            BZ_KCHECK(e);
    k_rle2_scan<<<(nb + 7) / 8, 256, 0, st>>>(p, nb);    BZ_KCHECK(e);
    k_rle2_emit<<<gt, 128, 0, st>>>(p);                  BZ_KCHECK(e);
    return 0;
