@@ -22,7 +22,8 @@ class Stats(C.Structure):
                 ("n_windows", C.c_uint32), ("sum_nblock", C.c_uint64), ("sum_nmtf", C.c_uint64),
                 ("n_power_blocks", C.c_uint32), ("combined_crc", C.c_uint32),
                 ("ms_total", C.c_float), ("ms_s1", C.c_float), ("ms_s2", C.c_float), ("ms_s3", C.c_float),
-                ("ms_s4", C.c_float), ("bwt_rounds", C.c_uint32), ("kernel_launches", C.c_uint32), ("out_bits", C.c_uint64)]
+                ("ms_s4", C.c_float), ("bwt_rounds", C.c_uint32), ("kernel_launches", C.c_uint32), ("out_bits", C.c_uint64),
+                ("ms_span", C.c_float)]
 
 
 class BzStream(C.Structure):

@@ -38,6 +38,7 @@ struct MWorker {
    u8* dbuf[2]; size_t dcap; int cur;               // device input staging (host sources)
    size_t pf_lo, pf_hi, pf_core_b, pf_core_e; bool pf_valid;   // prefetch: start range of the next window, the bytes already copied
    cudaStream_t copy_stream; cudaEvent_t ev_pf;
+   cudaEvent_t ev_j0, ev_j1; float span_ms;          // the job as this engine's stream saw it
    u8* d_shift; u8* h_seam;                          // shifted output; pinned scratch for the seam bytes
 };
 
@@ -145,6 +146,8 @@ static int run_job(MWorker* wk)
    wk->pf_valid = false;
    // the output buffer is cleared here and again as soon as a window's output has left it -- not in front of stage 1 of
    // the next window, where the clear would sit on the chain every other engine waits for
+   wk->span_ms = 0.f;
+   BZ_CUDA(e, cudaEventRecord(wk->ev_j0, st));
    BZ_CUDA(e, cudaMemsetAsync(e->d_out, 0, e->out_cap, st));
    double t_wait_a = 0, t_wait_b = 0, t_s1 = 0, t_job0 = now_s();
    u32 n_win = 0;
@@ -252,6 +255,9 @@ static int run_job(MWorker* wk)
       pthread_mutex_unlock(&J.mu);
       if (fin) break;
    }
+   BZ_CUDA(e, cudaEventRecord(wk->ev_j1, st));
+   BZ_CUDA(e, cudaEventSynchronize(wk->ev_j1));
+   if (cudaEventElapsedTime(&wk->span_ms, wk->ev_j0, wk->ev_j1) != cudaSuccess) { cudaGetLastError(); wk->span_ms = 0.f; }
    {
       // BZ2_B200_MULTI_TRACE=1: where this engine's time went (waiting for its window's start / for its output offset,
       // stage 1 incl. its host round trip, everything else)
@@ -303,6 +309,8 @@ static void multi_free(Multi* m)
          if (w.copy_stream) cudaStreamDestroy(w.copy_stream);
          if (w.e->s1_stream) { cudaStreamDestroy(w.e->s1_stream); w.e->s1_stream = nullptr; }
          if (w.ev_pf) cudaEventDestroy(w.ev_pf);
+         if (w.ev_j0) cudaEventDestroy(w.ev_j0);
+         if (w.ev_j1) cudaEventDestroy(w.ev_j1);
          engine_free(w.e);
       }
    }
@@ -355,6 +363,7 @@ int bz2b200_multi_create(bz2b200_multi** out, const int* devices, int n_engines,
          e->hp_late = 1u;
       }
       ok = ok && cudaEventCreateWithFlags(&w.ev_pf, cudaEventDisableTiming) == cudaSuccess;
+      ok = ok && cudaEventCreate(&w.ev_j0) == cudaSuccess && cudaEventCreate(&w.ev_j1) == cudaSuccess;
       if (!ok) { cudaGetLastError(); rc = set_err(BZ2B200_ENOMEM, "device allocation failed (multi-engine staging)"); break; }
       if (pthread_create(&w.th, nullptr, worker_main, &w) != 0) { rc = set_err(BZ2B200_ENOMEM, "cannot start an engine thread"); break; }
       w.started = true;
@@ -439,6 +448,7 @@ int bz2b200_multi_compress(bz2b200_multi* h, const void* src, const void* const*
          t.n_power_blocks += s.n_power_blocks;
          t.ms_total += s.ms_total; t.ms_s1 += s.ms_s1; t.ms_s2 += s.ms_s2; t.ms_s3 += s.ms_s3; t.ms_s4 += s.ms_s4;
          t.bwt_rounds += s.bwt_rounds; t.kernel_launches += s.kernel_launches;
+         if (m->w[k].span_ms > t.ms_span) t.ms_span = m->w[k].span_ms;
       }
       t.in_bytes = n; t.out_bytes = *dst_len; t.combined_crc = J.b_crc; t.out_bits = bit;
       *stats = t;

@@ -63,6 +63,8 @@ typedef struct {
    uint32_t bwt_rounds;          /* prefix-doubling rounds, summed over windows              */
    uint32_t kernel_launches;
    uint64_t out_bits;            /* exact bit length of what was produced (segment mode: not padded)   */
+   float    ms_span;             /* bz2b200_multi_compress: duration of the job ON THE DEVICES -- CUDA events on every
+                                    engine's stream at the start of the job and after its last copy, max over engines */
 } bz2b200_stats;
 
 int  bz2b200_device_count(void);
