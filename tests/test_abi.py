@@ -100,3 +100,15 @@ def test_multi_param_errors_need_no_gpu(lib):
 def test_version_strings(lib):
     assert lib.BZ2_bzlibVersion().startswith(b"1.0.6")
     assert b"sm_100a" in lib.bz2b200_version()
+
+
+def test_stats_struct_matches_the_header(tmp_path):
+    """binding.Stats mirrors bz2b200_stats field for field: a size or offset mismatch would let the library write past it."""
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "bz2_b200.h"\nint main(void){printf("%zu %zu %zu %zu\\n", sizeof(bz2b200_stats), '
+                   'offsetof(bz2b200_stats, ms_total), offsetof(bz2b200_stats, out_bits), offsetof(bz2b200_stats, ms_span));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    size, o_total, o_bits, o_span = map(int, subprocess.check_output([str(exe)]).split())
+    assert C.sizeof(binding.Stats) == size
+    assert binding.Stats.ms_total.offset == o_total and binding.Stats.out_bits.offset == o_bits and binding.Stats.ms_span.offset == o_span
